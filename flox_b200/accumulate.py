@@ -1,0 +1,116 @@
+"""Wide device-side accumulators for one grouped-reduction problem.
+
+One `GroupedAccumulators` covers a list of chunks `values[A, n_k, B]` + `codes[n_k]` that are to
+be reduced TOGETHER into `[A, B, G]` bins: a single numpy-style call has one chunk, flox's
+map-reduce over the chunks resident on this GPU has many (the per-chunk `chunk_reduce` and the
+`_simple_combine` of flox/dask.py:90-144 fuse into one accumulation).  Each kernel family runs at
+most ONE pass over the data and is cached, so `mean` (= sum + nanlen in the reference,
+flox/aggregations.py:328-336) or `nanmax` + its min_count `nanlen` (aggregations.py:997-1014)
+cost one read of the inputs, not two.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+from .kernels import acc_dtype, get_kernels
+
+
+class GroupedAccumulators:
+    def __init__(self, chunks: Sequence[tuple[torch.Tensor, torch.Tensor]], A: int, B: int, G: int,
+                 value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None):
+        self.chunks = list(chunks)
+        self.A, self.B, self.G = int(A), int(B), int(G)
+        self.nbins = self.A * self.B * self.G
+        self.value_dtype = value_dtype
+        self.device = device
+        if index_base is None:
+            index_base, pos = [], 0
+            for _, c in self.chunks:
+                index_base.append(pos)
+                pos += c.numel()
+        self.index_base = list(index_base)
+        self._moments: dict[tuple, tuple] = {}
+        self._fchunks = None
+        self._minmax: dict[bool, tuple] = {}
+        self._var: dict[bool, tuple] = {}
+        self._arg: dict[tuple, torch.Tensor] = {}
+        self.k = get_kernels()
+
+    # ---- allocation ----------------------------------------------------------------------
+    def _i64(self):
+        return torch.empty(self.nbins, dtype=torch.int64, device=self.device)
+
+    def _f64(self):
+        return torch.empty(self.nbins, dtype=torch.float64, device=self.device)
+
+    # ---- kernel families -----------------------------------------------------------------
+    def _chunks_as(self, as_float: bool):
+        """Integer values that feed a FLOAT result are summed as float64, like the reference's
+        `ufunc.reduceat(..., dtype=float64)` (flox/aggregate_flox.py:183-190): converted once, cached."""
+        if not as_float or self.value_dtype.is_floating_point:
+            return self.chunks, self.value_dtype
+        if self._fchunks is None:
+            self._fchunks = [(v.to(torch.float64), c) for v, c in self.chunks]
+        return self._fchunks, torch.float64
+
+    def moments(self, op: int = L.OP_SUM, as_float: bool = False):
+        """(acc, cnt, nnan): acc = op over non-NaN values, cnt/nnan = # non-NaN / NaN values."""
+        as_float = bool(as_float) and not self.value_dtype.is_floating_point
+        if (op, as_float) not in self._moments:
+            chunks, vdt = self._chunks_as(as_float)
+            acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
+            cnt, nnan = self._i64(), self._i64()
+            self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
+            self._moments[(op, as_float)] = (acc, cnt, nnan)
+        return self._moments[(op, as_float)]
+
+    def minmax(self, is_max: bool):
+        if is_max not in self._minmax:
+            key, cnt, nnan = self._i64(), self._i64(), self._i64()
+            self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
+                          value_dtype=self.value_dtype)
+            self._minmax[is_max] = (key, cnt, nnan)
+        return self._minmax[is_max]
+
+    def counts(self):
+        """(cnt, nnan) from whichever pass already ran, else from a SUM pass."""
+        for store in (self._moments, self._minmax):
+            for v in store.values():
+                return v[1], v[2]
+        _, cnt, nnan = self.moments(L.OP_SUM)
+        return cnt, nnan
+
+    def var(self, skipna: bool):
+        """(m2, s_acc, cnt, nnan): two-pass centred sum of squared deviations (var_chunk).
+        Always a float computation: integer values go through float64 (aggregations.py:352-387)."""
+        if skipna not in self._var:
+            chunks, vdt = self._chunks_as(True)
+            acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True)
+            means, m2 = self._f64(), self._f64()
+            self.k.group_means(vdt, acc, cnt, nnan, skipna, means)
+            self.k.sqdev(chunks, self.A, self.B, self.G, means, skipna, m2, init=True, value_dtype=vdt)
+            self._var[skipna] = (m2, acc, cnt, nnan)
+        return self._var[skipna]
+
+    def argext(self, is_max: bool, skipna: bool):
+        key_ = (is_max, skipna)
+        if key_ not in self._arg:
+            key, cnt, nnan = self.minmax(is_max)
+            idx = self._i64()
+            self.k.argext(self.chunks, self.A, self.B, self.G, key, nnan, skipna, self.index_base, idx, init=True,
+                          value_dtype=self.value_dtype)
+            self._arg[key_] = idx
+        return self._arg[key_]
+
+    # ---- typed results -------------------------------------------------------------------
+    def shape(self, lead: tuple[int, ...] = ()):
+        return tuple(lead) + (self.G,)
+
+    def finalize(self, kind: int, acc, acc2, cnt, nnan, *, skipna: bool, out_dtype: torch.dtype, fill=None,
+                 min_count: int = 0, mc_fill=None, ddof: int = 0, value_dtype=None) -> torch.Tensor:
+        out = torch.empty(self.nbins, dtype=out_dtype, device=self.device)
+        self.k.finalize(kind, value_dtype or self.value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out)
+        return out

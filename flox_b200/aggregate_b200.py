@@ -1,0 +1,108 @@
+"""engine="b200": drop-in for the reference's engine modules.
+
+Every function has the engine contract of flox/aggregate_flox.py:133-143 (identical in
+aggregate_npg.py:58 and aggregate_numbagg.py:42-52):
+
+    f(group_idx, array, *, axis=-1, size=None, fill_value=None, dtype=None, **kw) -> array[..., size]
+
+`group_idx` is 1-D integer codes over the LAST axis of `array`; codes outside [0, size) are
+ignored; groups without rows hold `fill_value`; the result dtype is `dtype` or `array.dtype`
+(aggregate_flox.py:171-180).  Inputs may be numpy arrays (copied to the GPU) or torch tensors
+(used in place when already on the GPU); the result comes back in the same container kind.
+Unlike engine="flox" the codes need NOT be sorted: the CUDA kernels are scatter reductions, so
+core.chunk_reduce skips `_prepare_for_flox` (flox/core.py:336-339) for this engine.
+
+`generic_aggregate(..., engine="b200")` resolves these by name exactly as
+flox/aggregations.py:85-90 does for engine="flox".
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .accumulate import GroupedAccumulators
+from .arrays import from_device, is_torch, kernel_dtype, np_dtype_of, to_device, torch_dtype
+from .kernels import default_device
+from .reductions import evaluate
+
+__all__ = [
+    "sum", "nansum", "prod", "nanprod", "max", "nanmax", "min", "nanmin", "nanlen", "mean", "nanmean",
+    "sum_of_squares", "nansum_of_squares", "argmax", "argmin", "nanargmax", "nanargmin", "var", "nanvar", "std", "nanstd",
+]
+
+
+def _codes_to_device(group_idx, device):
+    t = to_device(group_idx, device)
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.to(torch.int64)
+    return t.reshape(-1)
+
+
+def make_accumulators(group_idx, array, size=None) -> tuple[GroupedAccumulators, tuple[int, ...], int]:
+    """Device accumulators for one `(…, N)` array + `(N,)` codes problem."""
+    device = default_device()
+    np_dt = np_dtype_of(array)
+    vals = to_device(array, device)
+    kdt = kernel_dtype(vals.dtype)
+    if vals.dtype != kdt:
+        vals = vals.to(kdt)
+    codes = _codes_to_device(group_idx, device)
+    if vals.ndim == 0 or vals.shape[-1] != codes.numel():
+        raise ValueError("array.shape[-1] must equal len(group_idx)")
+    if size is None:
+        size = int(codes.max().item()) + 1 if codes.numel() else 0
+    lead = tuple(vals.shape[:-1])
+    A = math.prod(lead)
+    acc = GroupedAccumulators([(vals.reshape(A, -1, 1), codes)], A, 1, int(size), kdt, device)
+    acc.np_dtype = np_dt
+    return acc, lead, int(size)
+
+
+def _engine(func: str, default_int_to_float: bool = False, fixed_dtype=None):
+    def kernel(group_idx, array, *, axis=-1, size=None, fill_value=None, dtype=None, **kwargs):
+        if axis not in (-1, np.ndim(array) - 1):
+            raise ValueError("the b200 engine reduces along the last axis (as chunk_reduce always asks)")
+        acc, lead, size = make_accumulators(group_idx, array, size)
+        if dtype is not None:
+            out_dt = np.dtype(dtype)
+        elif fixed_dtype is not None:
+            out_dt = np.dtype(fixed_dtype)
+        else:
+            out_dt = acc.np_dtype
+            if default_int_to_float and out_dt.kind in "iub":
+                out_dt = np.dtype("float64")
+            elif out_dt.kind == "b":
+                out_dt = np.dtype("int64")
+        ddof = kwargs.pop("ddof", 0)
+        res = evaluate(acc, func, out_dtype=out_dt, fill_value=fill_value, ddof=ddof)
+        return from_device(res.reshape(lead + (size,)), array, out_dt)
+
+    kernel.__name__ = func
+    kernel.__qualname__ = func
+    kernel.__doc__ = f"Grouped `{func}` on the GPU; engine contract of flox/aggregate_flox.py:133-143."
+    return kernel
+
+
+sum = _engine("sum")
+nansum = _engine("nansum")
+prod = _engine("prod")
+nanprod = _engine("nanprod")
+max = _engine("max")
+nanmax = _engine("nanmax")
+min = _engine("min")
+nanmin = _engine("nanmin")
+sum_of_squares = _engine("sum_of_squares")
+nansum_of_squares = _engine("nansum_of_squares")
+nanlen = _engine("nanlen", fixed_dtype=np.int64)
+mean = _engine("mean", default_int_to_float=True)
+nanmean = _engine("nanmean", default_int_to_float=True)
+var = _engine("var", default_int_to_float=True)
+nanvar = _engine("nanvar", default_int_to_float=True)
+std = _engine("std", default_int_to_float=True)
+nanstd = _engine("nanstd", default_int_to_float=True)
+argmax = _engine("argmax", fixed_dtype=np.int64)
+argmin = _engine("argmin", fixed_dtype=np.int64)
+nanargmax = _engine("nanargmax", fixed_dtype=np.int64)
+nanargmin = _engine("nanargmin", fixed_dtype=np.int64)

@@ -1,0 +1,108 @@
+"""`ChunkedArray`: the stand-in for a dask array on the map-reduce path.
+
+flox hands `dask_groupby_agg` (flox/dask.py:325) a dask array whose blocks along the reduced axis
+become one `chunk_reduce` task each.  dask is not a dependency here; a ChunkedArray is simply the
+list of those blocks — slabs `[..., n_k]` along the LAST axis (numpy arrays, or torch tensors that
+may already live on the GPU) — plus the matching slabs of the labels.  `groupby_reduce` accepts it
+wherever the reference accepts a dask array.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .arrays import is_torch, np_dtype_of
+
+
+class ChunkedArray:
+    def __init__(self, chunks: Sequence):
+        chunks = list(chunks)
+        if not chunks:
+            raise ValueError("ChunkedArray needs at least one chunk")
+        lead = tuple(chunks[0].shape[:-1])
+        for c in chunks:
+            if tuple(c.shape[:-1]) != lead:
+                raise ValueError("chunks must agree on all but the last axis")
+        self.chunks = chunks
+
+    # -- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_array(cls, array, chunksize: int) -> "ChunkedArray":
+        n = array.shape[-1]
+        return cls([array[..., lo:min(lo + chunksize, n)] for lo in range(0, max(n, 1), chunksize)])
+
+    # -- array-ish surface -------------------------------------------------------------------
+    @property
+    def nchunks(self) -> int:
+        return len(self.chunks)
+
+    @property
+    def chunk_sizes(self) -> tuple[int, ...]:
+        return tuple(int(c.shape[-1]) for c in self.chunks)
+
+    @property
+    def shape(self) -> tuple[int, ...]:
+        return tuple(self.chunks[0].shape[:-1]) + (sum(self.chunk_sizes),)
+
+    @property
+    def ndim(self) -> int:
+        return self.chunks[0].ndim
+
+    @property
+    def dtype(self):
+        return np_dtype_of(self.chunks[0])
+
+    def map(self, fn) -> "ChunkedArray":
+        return ChunkedArray([fn(c) for c in self.chunks])
+
+    def astype(self, dt):
+        return self.map(lambda c: c.astype(dt))
+
+    def to(self, dt):
+        return self.map(lambda c: c.to(dt) if is_torch(c) else c.astype(str(dt).replace("torch.", "")))
+
+    def view(self, dt):
+        return self.map(lambda c: c.view(dt))
+
+    def rechunk_like(self, other: "ChunkedArray") -> "ChunkedArray":
+        if self.chunk_sizes == other.chunk_sizes:
+            return self
+        whole = self.concatenate()
+        out, lo = [], 0
+        for n in other.chunk_sizes:
+            out.append(whole[..., lo:lo + n])
+            lo += n
+        return ChunkedArray(out)
+
+    def concatenate(self):
+        if is_torch(self.chunks[0]):
+            return torch.cat(list(self.chunks), dim=-1)
+        return np.concatenate(self.chunks, axis=-1)
+
+    # -- labels ------------------------------------------------------------------------------
+    @staticmethod
+    def factorize_chunks(bys, expected_groups, sort: bool = True):
+        """Per-chunk factorization against KNOWN expected groups (flox/factorize.py:241-268:
+        the `any_by_dask` branch maps `_lazy_factorize_wrapper` over blocks)."""
+        from .factorize import _factorize_multiple
+
+        template = next(b for b in bys if is_chunked(b))
+        per_by_chunks = []
+        for b in bys:
+            if is_chunked(b):
+                per_by_chunks.append(b.rechunk_like(template).chunks)
+            else:
+                cb = ChunkedArray.from_array(b, 1).rechunk_like(template) if b.shape[-1] != 0 else None
+                per_by_chunks.append(cb.chunks)
+        out_chunks, found, grp_shape = [], None, None
+        for parts in zip(*per_by_chunks):
+            (codes,), found, grp_shape = _factorize_multiple(tuple(parts), expected_groups, sort=sort)
+            out_chunks.append(codes)
+        return (ChunkedArray(out_chunks),), found, grp_shape
+
+
+def is_chunked(x) -> bool:
+    return isinstance(x, ChunkedArray)

@@ -1,0 +1,177 @@
+// flox_b200 — shared device helpers for the grouped-reduction kernels (sm_100a).
+//
+// Data model (mirrors what flox.core.chunk_reduce hands an engine, reference
+// flox/core.py:298-316,368-370): a chunk is `values[A, n, B]` (C-contiguous; A = kept
+// leading dims, n = the reduced axis, B = kept trailing dims) plus integer group codes
+// `codes[n]` shared by every (a, b).  Codes outside [0, G) are skipped — that is what the
+// reference's "-1 -> sentinel bin -> strip" dance (flox/factorize.py:201-210,
+// flox/core.py:381-383) amounts to.  Accumulators are laid out `[A, B, G]`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/flox_b200.h"
+
+namespace floxb {
+
+constexpr int kMaxChunksPerLaunch = 48;
+
+// Chunk table passed BY VALUE in kernel parameter space (no device allocation, no copy).
+struct ChunkTable {
+  const void* values[kMaxChunksPerLaunch];
+  const void* codes[kMaxChunksPerLaunch];
+  int64_t n[kMaxChunksPerLaunch];            // reduced length of each chunk
+  int64_t tile_prefix[kMaxChunksPerLaunch + 1];  // exclusive prefix of per-chunk tile counts
+  int nchunks;
+};
+
+template <typename T> struct is_float { static constexpr bool value = false; };
+template <> struct is_float<float> { static constexpr bool value = true; };
+template <> struct is_float<double> { static constexpr bool value = true; };
+
+// Wide accumulator per value type: floats accumulate in f64 (the reference keeps f32 and
+// relies on pairwise reduceat, flox/aggregations.py:962-968; f64 + one final rounding is at
+// least as accurate), integers in int64 (flox/xrdtypes.py:175-185).
+template <typename T> struct Acc { using type = double; };
+template <> struct Acc<int32_t> { using type = long long; };
+template <> struct Acc<int64_t> { using type = long long; };
+
+template <typename T> __device__ __forceinline__ bool is_nan(T) { return false; }
+template <> __device__ __forceinline__ bool is_nan<float>(float v) { return v != v; }
+template <> __device__ __forceinline__ bool is_nan<double>(double v) { return v != v; }
+
+// ---- streaming loads (read-once data: bypass L1 allocation) -----------------------------
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ longlong2 ldg_stream(const longlong2* p) {
+  longlong2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+// Load 4 consecutive elements of T starting at a 16-byte-aligned (for 4-byte T) or
+// 32-byte-aligned-pair (for 8-byte T: two 16-byte loads) address.
+template <typename T> struct Vec4 { T v[4]; };
+
+template <typename T> __device__ __forceinline__ Vec4<T> load4(const T* p);
+template <> __device__ __forceinline__ Vec4<float> load4<float>(const float* p) {
+  float4 r = ldg_stream(reinterpret_cast<const float4*>(p));
+  return {{r.x, r.y, r.z, r.w}};
+}
+template <> __device__ __forceinline__ Vec4<int32_t> load4<int32_t>(const int32_t* p) {
+  int4 r = ldg_stream(reinterpret_cast<const int4*>(p));
+  return {{r.x, r.y, r.z, r.w}};
+}
+template <> __device__ __forceinline__ Vec4<int64_t> load4<int64_t>(const int64_t* p) {
+  longlong2 a = ldg_stream(reinterpret_cast<const longlong2*>(p));
+  longlong2 b = ldg_stream(reinterpret_cast<const longlong2*>(p) + 1);
+  return {{(int64_t)a.x, (int64_t)a.y, (int64_t)b.x, (int64_t)b.y}};
+}
+template <> __device__ __forceinline__ Vec4<double> load4<double>(const double* p) {
+  double2 a = ldg_stream(reinterpret_cast<const double2*>(p));
+  double2 b = ldg_stream(reinterpret_cast<const double2*>(p) + 1);
+  return {{a.x, a.y, b.x, b.y}};
+}
+
+// ---- order-preserving integer keys for float min/max ------------------------------------
+// Signed-integer order of the key equals the numeric order of the float, so the NATIVE
+// 32-bit shared-memory ATOMS.MAX/MIN.S32 can be used for f32 (f64 uses a 64-bit CAS loop).
+__device__ __forceinline__ int32_t f32_key(float f) {
+  int32_t b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float f32_unkey(int32_t k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ long long f64_key(double d) {
+  long long b = __double_as_longlong(d);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double f64_unkey(long long k) {
+  return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL));
+}
+
+// Key type / conversion per value type (ints are their own keys).
+template <typename T> struct Key;
+template <> struct Key<float> {
+  using type = int32_t;
+  static __device__ __forceinline__ type enc(float v) { return f32_key(v); }
+  static __device__ __forceinline__ float dec(type k) { return f32_unkey(k); }
+  static constexpr type lowest = INT32_MIN, highest = INT32_MAX;
+};
+template <> struct Key<int32_t> {
+  using type = int32_t;
+  static __device__ __forceinline__ type enc(int32_t v) { return v; }
+  static __device__ __forceinline__ int32_t dec(type k) { return k; }
+  static constexpr type lowest = INT32_MIN, highest = INT32_MAX;
+};
+template <> struct Key<double> {
+  using type = long long;
+  static __device__ __forceinline__ type enc(double v) { return f64_key(v); }
+  static __device__ __forceinline__ double dec(type k) { return f64_unkey(k); }
+  static constexpr type lowest = INT64_MIN, highest = INT64_MAX;
+};
+template <> struct Key<int64_t> {
+  using type = long long;
+  static __device__ __forceinline__ type enc(int64_t v) { return (long long)v; }
+  static __device__ __forceinline__ int64_t dec(type k) { return (int64_t)k; }
+  static constexpr type lowest = INT64_MIN, highest = INT64_MAX;
+};
+
+// ---- atomics ------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_mul(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(__longlong_as_double((long long)assumed) * v));
+  } while (old != assumed);
+}
+__device__ __forceinline__ void atomic_mul(long long* addr, long long v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a, assumed;
+  do {
+    assumed = old;
+    old = atomicCAS(a, assumed, (unsigned long long)((long long)assumed * v));
+  } while (old != assumed);
+}
+__device__ __forceinline__ void atomic_add(double* a, double v) { atomicAdd(a, v); }
+__device__ __forceinline__ void atomic_add(long long* a, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v);
+}
+
+// Map a flat persistent tile index onto (chunk, tile-within-chunk).
+__device__ __forceinline__ int find_chunk(const ChunkTable& t, int64_t tile) {
+  int lo = 0, hi = t.nchunks - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (t.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace floxb

@@ -1,0 +1,216 @@
+// Grouped max / min of the non-NaN values (as order-preserving integer keys) + counts, one pass.
+// Replaces aggregate_flox.max/min (np.maximum/minimum.reduceat, flox/aggregate_flox.py:214-217)
+// and the NaN->identity substitution of nanmax/nanmin (flox/aggregate_flox.py:195-207).
+//
+// f32 / i32 values use the NATIVE 32-bit shared-memory ATOMS.MAX/MIN.S32 on an order-preserving
+// key; f64 / i64 use a 64-bit CAS loop.  NaN rows never touch the key bin: they bump a NaN
+// counter, and floxb_finalize decides between propagate (max/min) and skip (nanmax/nanmin).
+#include "common.cuh"
+
+namespace floxb {
+
+template <typename K, bool IS_MAX> __device__ __forceinline__ void key_update(K* slot, K k) {
+  if constexpr (IS_MAX) atomicMax(slot, k); else atomicMin(slot, k);
+}
+
+template <typename VT, typename CT, bool IS_MAX, int THREADS, int ITERS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, long long* __restrict__ gkey,
+              unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
+  using K = typename Key<VT>::type;
+  constexpr int TILE = THREADS * 4 * ITERS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K* skey = reinterpret_cast<K*>(smem_raw);
+  unsigned* scnt = reinterpret_cast<unsigned*>(skey + G);
+  unsigned* snan = scnt + G;
+  const K ident = IS_MAX ? Key<VT>::lowest : Key<VT>::highest;
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    skey[g] = ident;
+    scnt[g] = 0u;
+    snan[g] = 0u;
+  }
+  __syncthreads();
+
+  auto accum = [&](VT v, CT c) {
+    if ((unsigned long long)c < (unsigned long long)G) {
+      if (is_nan(v)) {
+        atomicAdd(&snan[(int)c], 1u);
+      } else {
+        key_update<K, IS_MAX>(&skey[(int)c], Key<VT>::enc(v));
+        atomicAdd(&scnt[(int)c], 1u);
+      }
+    }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int ch = find_chunk(tab, tile);
+    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
+    const int64_t n = tab.n[ch];
+    const VT* __restrict__ vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
+    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
+    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
+    if (rows == TILE && aligned) {
+      Vec4<VT> v[ITERS];
+      Vec4<CT> c[ITERS];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int off = (it * THREADS + threadIdx.x) * 4;
+        v[it] = load4<VT>(vals + off);
+        c[it] = load4<CT>(codes + off);
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
+    }
+  }
+  __syncthreads();
+
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    const unsigned c = scnt[g];
+    if (c) {
+      key_update<long long, IS_MAX>(&gkey[g], (long long)skey[g]);
+      atomicAdd(&gcnt[g], (unsigned long long)c);
+    }
+    const unsigned m = snan[g];
+    if (m) atomicAdd(&gnan[g], (unsigned long long)m);
+  }
+}
+
+template <typename VT, typename CT, bool IS_MAX>
+__global__ void __launch_bounds__(256)
+k_minmax_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
+                long long* __restrict__ gkey, unsigned long long* __restrict__ gcnt,
+                unsigned long long* __restrict__ gnan) {
+  const int64_t row_len = n * B;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    const VT* __restrict__ row = vals + a * row_len;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
+      int64_t i, b;
+      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+      const CT c = codes[i];
+      if ((unsigned long long)c >= (unsigned long long)G) continue;
+      const VT v = row[j];
+      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      if (is_nan(v)) {
+        atomicAdd(&gnan[bin], 1ull);
+      } else {
+        key_update<long long, IS_MAX>(&gkey[bin], (long long)Key<VT>::enc(v));
+        atomicAdd(&gcnt[bin], 1ull);
+      }
+    }
+  }
+}
+
+__global__ void k_fill_key(long long* key, unsigned long long* cnt, unsigned long long* nnan, int64_t nbins,
+                           long long ident) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (int64_t)gridDim.x * blockDim.x) {
+    key[i] = ident;
+    if (cnt) cnt[i] = 0ull;
+    if (nnan) nnan[i] = 0ull;
+  }
+}
+
+constexpr int kMMThreads = 1024;
+constexpr int kMMIters = 2;
+constexpr size_t kMMSmemBudget = 227 * 1024;
+
+template <typename VT, typename CT, bool IS_MAX>
+int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, int64_t* acc_key,
+                  int64_t* cnt, int64_t* nnan, int init, int force_path, cudaStream_t st) {
+  using K = typename Key<VT>::type;
+  const int64_t nbins = A * B * G;
+  auto* gkey = reinterpret_cast<long long*>(acc_key);
+  auto* gcnt = reinterpret_cast<unsigned long long*>(cnt);
+  auto* gnan = reinterpret_cast<unsigned long long*>(nnan);
+  if (init && nbins > 0) {
+    const int blocks = (int)((nbins + 255) / 256 < 1184 ? (nbins + 255) / 256 : 1184);
+    k_fill_key<<<blocks, 256, 0, st>>>(gkey, gcnt, gnan, nbins, IS_MAX ? INT64_MIN : INT64_MAX);
+  }
+  if (nbins == 0) return FLOXB_OK;
+  const size_t smem = (size_t)G * (sizeof(K) + 8);
+  bool use_smem = (A == 1 && B == 1 && smem <= kMMSmemBudget);
+  if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
+  if (force_path == 2) use_smem = false;
+  if (use_smem) {
+    constexpr int TILE = kMMThreads * 4 * kMMIters;
+    auto kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMMSmemBudget) != cudaSuccess)
+      return FLOXB_ECUDA;
+    for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
+      ChunkTable tab;
+      const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
+      tab.nchunks = m;
+      tab.tile_prefix[0] = 0;
+      for (int k = 0; k < m; ++k) {
+        const floxb_chunk_t& ch = chunks[c0 + k];
+        if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+        tab.values[k] = ch.values;
+        tab.codes[k] = ch.codes;
+        tab.n[k] = ch.n;
+        tab.tile_prefix[k + 1] = tab.tile_prefix[k] + (ch.n + TILE - 1) / TILE;
+      }
+      const int64_t tiles = tab.tile_prefix[m];
+      if (tiles == 0) continue;
+      if (tiles / sm_count() * TILE >= (int64_t)1 << 32) return FLOXB_ERANGE;
+      const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+      kern<<<grid, kMMThreads, smem, st>>>(tab, tiles, (int)G, gkey, gcnt, gnan);
+    }
+  } else {
+    for (int64_t k = 0; k < n_chunks; ++k) {
+      const floxb_chunk_t& ch = chunks[k];
+      if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+      if (ch.n == 0) continue;
+      const int64_t row_len = ch.n * B;
+      int64_t bx = (row_len + 255) / 256;
+      const int64_t cap = (int64_t)sm_count() * 16;
+      if (bx > cap) bx = cap;
+      const int by = (int)(A < 65535 ? A : 65535);
+      if (bx * by > cap * 4) bx = (cap * 4 + by - 1) / by;
+      if (bx < 1) bx = 1;
+      dim3 grid((unsigned)bx, (unsigned)by);
+      k_minmax_global<VT, CT, IS_MAX><<<grid, 256, 0, st>>>(reinterpret_cast<const VT*>(ch.values),
+                                                          reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, gkey,
+                                                          gcnt, gnan);
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+template <typename VT>
+int mm_dispatch(int code_dtype, int is_max, const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B,
+                int64_t G, int64_t* key, int64_t* cnt, int64_t* nnan, int init, int force_path, cudaStream_t st) {
+  if (code_dtype == FLOXB_I64) {
+    return is_max ? launch_minmax<VT, int64_t, true>(chunks, n_chunks, A, B, G, key, cnt, nnan, init, force_path, st)
+                  : launch_minmax<VT, int64_t, false>(chunks, n_chunks, A, B, G, key, cnt, nnan, init, force_path, st);
+  }
+  if (code_dtype == FLOXB_I32) {
+    return is_max ? launch_minmax<VT, int32_t, true>(chunks, n_chunks, A, B, G, key, cnt, nnan, init, force_path, st)
+                  : launch_minmax<VT, int32_t, false>(chunks, n_chunks, A, B, G, key, cnt, nnan, init, force_path, st);
+  }
+  return FLOXB_EDTYPE;
+}
+
+}  // namespace floxb
+
+using namespace floxb;
+
+extern "C" int floxb_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A,
+                            int64_t B, int64_t n_groups, int is_max, int64_t* acc_key, int64_t* cnt, int64_t* nnan,
+                            int init, int force_path, void* stream) {
+  if (n_chunks < 0 || A < 0 || B < 0 || n_groups < 0 || (n_chunks > 0 && !chunks)) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && (!acc_key || !cnt || !nnan)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (value_dtype) {
+    case FLOXB_F32: return mm_dispatch<float>(code_dtype, is_max, chunks, n_chunks, A, B, n_groups, acc_key, cnt, nnan, init, force_path, st);
+    case FLOXB_F64: return mm_dispatch<double>(code_dtype, is_max, chunks, n_chunks, A, B, n_groups, acc_key, cnt, nnan, init, force_path, st);
+    case FLOXB_I32: return mm_dispatch<int32_t>(code_dtype, is_max, chunks, n_chunks, A, B, n_groups, acc_key, cnt, nnan, init, force_path, st);
+    case FLOXB_I64: return mm_dispatch<int64_t>(code_dtype, is_max, chunks, n_chunks, A, B, n_groups, acc_key, cnt, nnan, init, force_path, st);
+  }
+  return FLOXB_EDTYPE;
+}

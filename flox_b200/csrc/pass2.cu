@@ -1,0 +1,270 @@
+// Second-pass kernels that need a per-group value from a first pass:
+//   * floxb_group_means + floxb_sqdev : var_chunk's sum of squared deviations about the group
+//     mean (flox/aggregations.py:348-389) — a numerically centred two-pass variance, exactly
+//     the reference's formulation (one-pass sum-of-squares would lose the tests' 1e12 offsets,
+//     tests/test_core.py:2287-2319).
+//   * floxb_argext : first position of the extremum per group (chunk_argreduce,
+//     flox/core.py:157-211; numpy first-occurrence semantics pinned by tests/test_core.py:388-408).
+#include "common.cuh"
+
+namespace floxb {
+
+template <typename VT>
+__global__ void k_group_means(const typename Acc<VT>::type* __restrict__ acc, const long long* __restrict__ cnt,
+                              const long long* __restrict__ nnan, int64_t nbins, int skipna, double* __restrict__ means) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (int64_t)gridDim.x * blockDim.x) {
+    double m;
+    if (!skipna && nnan[i] > 0) {
+      m = __longlong_as_double(0x7ff8000000000000LL);
+    } else if constexpr (is_float<VT>::value) {
+      // the reference divides in the array dtype: array_sums / array_lens (aggregations.py:375-376)
+      const VT s = (VT)acc[i];
+      m = (double)(VT)((double)s / (double)cnt[i]);
+    } else {
+      m = (double)acc[i] / (double)cnt[i];
+    }
+    means[i] = m;
+  }
+}
+
+// ---- squared deviations -----------------------------------------------------------------
+template <typename VT, typename CT, int THREADS, int ITERS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_sqdev_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, const double* __restrict__ means,
+             int skipna, double* __restrict__ gm2) {
+  constexpr int TILE = THREADS * 4 * ITERS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm2 = reinterpret_cast<double*>(smem_raw);
+  double* smean = sm2 + G;
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    sm2[g] = 0.0;
+    smean[g] = means[g];
+  }
+  __syncthreads();
+  auto accum = [&](VT v, CT c) {
+    if ((unsigned long long)c < (unsigned long long)G) {
+      if (is_nan(v) && skipna) return;
+      const double d = (double)v - smean[(int)c];
+      atomicAdd(&sm2[(int)c], d * d);
+    }
+  };
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int ch = find_chunk(tab, tile);
+    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
+    const int64_t n = tab.n[ch];
+    const VT* __restrict__ vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
+    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
+    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
+    if (rows == TILE && aligned) {
+      Vec4<VT> v[ITERS];
+      Vec4<CT> c[ITERS];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int off = (it * THREADS + threadIdx.x) * 4;
+        v[it] = load4<VT>(vals + off);
+        c[it] = load4<CT>(codes + off);
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    const double s = sm2[g];
+    if (s != 0.0) atomicAdd(&gm2[g], s);  // NaN != 0 is true: NaN propagates
+  }
+}
+
+template <typename VT, typename CT>
+__global__ void __launch_bounds__(256)
+k_sqdev_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
+               const double* __restrict__ means, int skipna, double* __restrict__ gm2) {
+  const int64_t row_len = n * B;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    const VT* __restrict__ row = vals + a * row_len;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
+      int64_t i, b;
+      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+      const CT c = codes[i];
+      if ((unsigned long long)c >= (unsigned long long)G) continue;
+      const VT v = row[j];
+      if (is_nan(v) && skipna) continue;
+      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      const double d = (double)v - means[bin];
+      atomicAdd(&gm2[bin], d * d);
+    }
+  }
+}
+
+// ---- arg-extremum ------------------------------------------------------------------------
+template <typename VT, typename CT>
+__global__ void __launch_bounds__(256)
+k_argext_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
+                const long long* __restrict__ key, const long long* __restrict__ nnan, int skipna, int64_t index_base,
+                long long* __restrict__ gidx) {
+  const int64_t row_len = n * B;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    const VT* __restrict__ row = vals + a * row_len;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
+      int64_t i, b;
+      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+      const CT c = codes[i];
+      if ((unsigned long long)c >= (unsigned long long)G) continue;
+      const VT v = row[j];
+      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      bool hit;
+      if (!skipna && nnan[bin] > 0) hit = is_nan(v);          // NaN propagates: first NaN wins
+      else hit = !is_nan(v) && (long long)Key<VT>::enc(v) == key[bin];
+      if (hit) atomicMin(&gidx[bin], (long long)(index_base + i));
+    }
+  }
+}
+
+__global__ void k_fill_i64(long long* p, int64_t n, long long v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_f64(double* p, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline dim3 generic_grid(int64_t row_len, int64_t A) {
+  int64_t bx = (row_len + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (bx > cap) bx = cap;
+  const int by = (int)(A < 65535 ? A : 65535);
+  if (bx * by > cap * 4) bx = (cap * 4 + by - 1) / by;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)by);
+}
+static inline int fill_blocks(int64_t n) { return (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184); }
+
+constexpr int kSqThreads = 1024;
+constexpr int kSqIters = 2;
+
+template <typename VT, typename CT>
+int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, const double* means,
+                 int skipna, double* m2, int init, cudaStream_t st) {
+  const int64_t nbins = A * B * G;
+  if (init && nbins > 0) k_fill_f64<<<fill_blocks(nbins), 256, 0, st>>>(m2, nbins, 0.0);
+  if (nbins == 0) return FLOXB_OK;
+  const size_t smem = (size_t)G * 16;
+  if (A == 1 && B == 1 && smem <= 227 * 1024) {
+    constexpr int TILE = kSqThreads * 4 * kSqIters;
+    auto kern = k_sqdev_smem<VT, CT, kSqThreads, kSqIters>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return FLOXB_ECUDA;
+    for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
+      ChunkTable tab;
+      const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
+      tab.nchunks = m;
+      tab.tile_prefix[0] = 0;
+      for (int k = 0; k < m; ++k) {
+        const floxb_chunk_t& ch = chunks[c0 + k];
+        if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+        tab.values[k] = ch.values;
+        tab.codes[k] = ch.codes;
+        tab.n[k] = ch.n;
+        tab.tile_prefix[k + 1] = tab.tile_prefix[k] + (ch.n + TILE - 1) / TILE;
+      }
+      const int64_t tiles = tab.tile_prefix[m];
+      if (tiles == 0) continue;
+      const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+      kern<<<grid, kSqThreads, smem, st>>>(tab, tiles, (int)G, means, skipna, m2);
+    }
+  } else {
+    for (int64_t k = 0; k < n_chunks; ++k) {
+      const floxb_chunk_t& ch = chunks[k];
+      if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+      if (ch.n == 0) continue;
+      k_sqdev_global<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(
+          reinterpret_cast<const VT*>(ch.values), reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, means, skipna, m2);
+    }
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+template <typename VT, typename CT>
+int launch_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, const int64_t* key,
+                  const int64_t* nnan, int skipna, const int64_t* index_base, int64_t* idx, int init, cudaStream_t st) {
+  const int64_t nbins = A * B * G;
+  if (init && nbins > 0) k_fill_i64<<<fill_blocks(nbins), 256, 0, st>>>(reinterpret_cast<long long*>(idx), nbins, INT64_MAX);
+  if (nbins == 0) return FLOXB_OK;
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    const floxb_chunk_t& ch = chunks[k];
+    if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+    if (ch.n == 0) continue;
+    k_argext_global<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(
+        reinterpret_cast<const VT*>(ch.values), reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G,
+        reinterpret_cast<const long long*>(key), reinterpret_cast<const long long*>(nnan), skipna,
+        index_base ? index_base[k] : 0, reinterpret_cast<long long*>(idx));
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+}  // namespace floxb
+
+using namespace floxb;
+
+#define FLOXB_DISPATCH_VT_CT(FN, ...)                                                          \
+  do {                                                                                         \
+    if (code_dtype == FLOXB_I64) {                                                             \
+      switch (value_dtype) {                                                                   \
+        case FLOXB_F32: return FN<float, int64_t>(__VA_ARGS__);                                \
+        case FLOXB_F64: return FN<double, int64_t>(__VA_ARGS__);                               \
+        case FLOXB_I32: return FN<int32_t, int64_t>(__VA_ARGS__);                              \
+        case FLOXB_I64: return FN<int64_t, int64_t>(__VA_ARGS__);                              \
+      }                                                                                        \
+    } else if (code_dtype == FLOXB_I32) {                                                      \
+      switch (value_dtype) {                                                                   \
+        case FLOXB_F32: return FN<float, int32_t>(__VA_ARGS__);                                \
+        case FLOXB_F64: return FN<double, int32_t>(__VA_ARGS__);                               \
+        case FLOXB_I32: return FN<int32_t, int32_t>(__VA_ARGS__);                              \
+        case FLOXB_I64: return FN<int64_t, int32_t>(__VA_ARGS__);                              \
+      }                                                                                        \
+    }                                                                                          \
+    return FLOXB_EDTYPE;                                                                       \
+  } while (0)
+
+extern "C" int floxb_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A,
+                           int64_t B, int64_t n_groups, const double* means, int skipna, double* acc_m2, int init,
+                           void* stream) {
+  if (n_chunks < 0 || A < 0 || B < 0 || n_groups < 0 || (n_chunks > 0 && !chunks)) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && (!means || !acc_m2)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FLOXB_DISPATCH_VT_CT(launch_sqdev, chunks, n_chunks, A, B, n_groups, means, skipna, acc_m2, init, st);
+}
+
+extern "C" int floxb_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A,
+                            int64_t B, int64_t n_groups, const int64_t* acc_key, const int64_t* nnan, int skipna,
+                            const int64_t* index_base, int64_t* acc_idx, int init, void* stream) {
+  if (n_chunks < 0 || A < 0 || B < 0 || n_groups < 0 || (n_chunks > 0 && !chunks)) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && (!acc_key || !nnan || !acc_idx)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FLOXB_DISPATCH_VT_CT(launch_argext, chunks, n_chunks, A, B, n_groups, acc_key, nnan, skipna, index_base, acc_idx, init, st);
+}
+
+extern "C" int floxb_group_means(int value_dtype, const void* acc, const int64_t* cnt, const int64_t* nnan, int64_t n_bins,
+                                 int skipna, double* means, void* stream) {
+  if (n_bins < 0) return FLOXB_EINVAL;
+  if (n_bins == 0) return FLOXB_OK;
+  if (!acc || !cnt || !nnan || !means) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = fill_blocks(n_bins);
+  const long long* c = reinterpret_cast<const long long*>(cnt);
+  const long long* m = reinterpret_cast<const long long*>(nnan);
+  switch (value_dtype) {
+    case FLOXB_F32: k_group_means<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const double*>(acc), c, m, n_bins, skipna, means); break;
+    case FLOXB_F64: k_group_means<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double*>(acc), c, m, n_bins, skipna, means); break;
+    case FLOXB_I32: k_group_means<int32_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(acc), c, m, n_bins, skipna, means); break;
+    case FLOXB_I64: k_group_means<int64_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(acc), c, m, n_bins, skipna, means); break;
+    default: return FLOXB_EDTYPE;
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}

@@ -1,0 +1,205 @@
+"""Kernel layer: torch tensors in, C-ABI calls out.
+
+`CudaKernels` is the only backend the package ships; every method is a thin, stream-ordered
+wrapper over one `floxb_*` entry point of include/flox_b200.h (torch supplies device memory
+and the current stream — plumbing only).  There is no CPU implementation here: without the
+built library and a CUDA device every call raises.  `set_backend` exists so that the test
+suite can check the HOST logic on a CPU-only machine with an emulator that lives under
+tests/ (never imported by the package).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib as L
+
+_TORCH2CODE = {torch.float32: L.F32, torch.float64: L.F64, torch.int32: L.I32, torch.int64: L.I64}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _TORCH2CODE[dt]
+    except KeyError:
+        raise TypeError(f"flox_b200 kernels take float32/float64/int32/int64, got {dt}") from None
+
+
+def acc_dtype(value_dtype: torch.dtype) -> torch.dtype:
+    """Wide accumulator dtype for a value dtype (f64 for floats, i64 for ints)."""
+    return torch.float64 if value_dtype.is_floating_point else torch.int64
+
+
+Chunks = Sequence[tuple[torch.Tensor, torch.Tensor]]  # (values[A, n, B], codes[n])
+
+
+class CudaKernels:
+    name = "cuda"
+
+    def __init__(self):
+        self.launches = 0  # number of C-ABI kernel entry calls issued (bench reports it)
+
+    # -- helpers ---------------------------------------------------------------------------
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _ptr(t: torch.Tensor | None) -> int:
+        return 0 if t is None else t.data_ptr()
+
+    @staticmethod
+    def _require_cuda(*tensors):
+        for t in tensors:
+            if t is not None and not t.is_cuda:
+                raise L.FloxB200Error("flox_b200 kernels need CUDA tensors (no CPU fallback)")
+
+    def _chunk_array(self, chunks: Chunks, A: int, B: int):
+        arr = (L.Chunk * len(chunks))()
+        vdt = cdt = None
+        for k, (v, c) in enumerate(chunks):
+            self._require_cuda(v, c)
+            if not v.is_contiguous() or not c.is_contiguous():
+                raise ValueError("chunks must be contiguous")
+            n = c.numel()
+            if v.numel() != A * n * B:
+                raise ValueError(f"values chunk has {v.numel()} elements, expected {A}*{n}*{B}")
+            if vdt is None:
+                vdt, cdt = v.dtype, c.dtype
+            elif (v.dtype, c.dtype) != (vdt, cdt):
+                raise TypeError("all chunks must share dtypes")
+            arr[k].values, arr[k].codes, arr[k].n = v.data_ptr(), c.data_ptr(), n
+        return arr, vdt, cdt
+
+    # -- reductions ------------------------------------------------------------------------
+    def moments(self, chunks: Chunks, A: int, B: int, G: int, op: int, acc, cnt, nnan, init=True, force_path=0):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(acc, cnt, nnan)
+        if vdt is None:
+            vdt, cdt = (torch.float64 if acc.dtype == torch.float64 else torch.int64), torch.int64
+        rc = L.load().floxb_moments(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, op, self._ptr(acc),
+                                    self._ptr(cnt), self._ptr(nnan), int(init), force_path, self._stream())
+        L.check(rc, "floxb_moments")
+        self.launches += 1
+
+    def minmax(self, chunks: Chunks, A: int, B: int, G: int, is_max: bool, key, cnt, nnan, init=True, force_path=0,
+               value_dtype=None):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(key, cnt, nnan)
+        if vdt is None:
+            vdt, cdt = value_dtype or torch.float64, torch.int64
+        rc = L.load().floxb_minmax(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, int(is_max),
+                                   self._ptr(key), self._ptr(cnt), self._ptr(nnan), int(init), force_path, self._stream())
+        L.check(rc, "floxb_minmax")
+        self.launches += 1
+
+    def sqdev(self, chunks: Chunks, A: int, B: int, G: int, means, skipna: bool, m2, init=True, value_dtype=None):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(means, m2)
+        if vdt is None:
+            vdt, cdt = value_dtype or torch.float64, torch.int64
+        rc = L.load().floxb_sqdev(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, self._ptr(means),
+                                  int(skipna), self._ptr(m2), int(init), self._stream())
+        L.check(rc, "floxb_sqdev")
+        self.launches += 1
+
+    def group_means(self, value_dtype, acc, cnt, nnan, skipna: bool, means):
+        self._require_cuda(acc, cnt, nnan, means)
+        rc = L.load().floxb_group_means(dtype_code(value_dtype), self._ptr(acc), self._ptr(cnt), self._ptr(nnan),
+                                        acc.numel(), int(skipna), self._ptr(means), self._stream())
+        L.check(rc, "floxb_group_means")
+        self.launches += 1
+
+    def argext(self, chunks: Chunks, A: int, B: int, G: int, key, nnan, skipna: bool, index_base: Sequence[int], idx,
+               init=True, value_dtype=None):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(key, nnan, idx)
+        if vdt is None:
+            vdt, cdt = value_dtype or torch.float64, torch.int64
+        base = (C.c_int64 * max(len(chunks), 1))(*[int(b) for b in index_base])
+        rc = L.load().floxb_argext(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, self._ptr(key),
+                                   self._ptr(nnan), int(skipna), base, self._ptr(idx), int(init), self._stream())
+        L.check(rc, "floxb_argext")
+        self.launches += 1
+
+    # -- epilogues -------------------------------------------------------------------------
+    def finalize(self, kind: int, value_dtype, acc, acc2, cnt, nnan, skipna: bool, fill, min_count: int, mc_fill,
+                 ddof: int, out):
+        self._require_cuda(acc, acc2, cnt, nnan, out)
+
+        def split(v):
+            if v is None:
+                return float("nan"), 0
+            fv = float(v)
+            try:
+                iv = int(v)
+            except (ValueError, OverflowError):  # nan / inf
+                iv = 0
+            return fv, iv
+
+        ff, fi = split(fill)
+        mf, mi = split(mc_fill)
+        rc = L.load().floxb_finalize(kind, dtype_code(value_dtype), dtype_code(out.dtype), self._ptr(acc), self._ptr(acc2),
+                                     self._ptr(cnt), self._ptr(nnan), out.numel(), int(skipna), ff, fi, int(min_count), mf,
+                                     mi, int(ddof), self._ptr(out), self._stream())
+        L.check(rc, "floxb_finalize")
+        self.launches += 1
+
+    def combine(self, kind: int, stacked, out):
+        self._require_cuda(stacked, out)
+        nblk = stacked.shape[0]
+        rc = L.load().floxb_combine(kind, dtype_code(stacked.dtype), self._ptr(stacked), nblk, out.numel(), self._ptr(out),
+                                    self._stream())
+        L.check(rc, "floxb_combine")
+        self.launches += 1
+
+    def var_combine(self, m2, s, n, out_m2, out_s, out_n):
+        self._require_cuda(m2, s, n, out_m2, out_s, out_n)
+        rc = L.load().floxb_var_combine(self._ptr(m2), self._ptr(s), self._ptr(n), m2.shape[0], out_m2.numel(),
+                                        self._ptr(out_m2), self._ptr(out_s), self._ptr(out_n), self._stream())
+        L.check(rc, "floxb_var_combine")
+        self.launches += 1
+
+    # -- label encoding --------------------------------------------------------------------
+    def digitize(self, labels, edges, closed_right: bool, codes):
+        self._require_cuda(labels, edges, codes)
+        rc = L.load().floxb_digitize(self._ptr(labels), dtype_code(labels.dtype), labels.numel(), self._ptr(edges),
+                                     edges.numel(), int(closed_right), self._ptr(codes), self._stream())
+        L.check(rc, "floxb_digitize")
+        self.launches += 1
+
+    def ravel_codes(self, c0, c1, size0: int, size1: int, out):
+        self._require_cuda(c0, c1, out)
+        rc = L.load().floxb_ravel_codes(self._ptr(c0), self._ptr(c1), c0.numel(), size0, size1, self._ptr(out),
+                                        self._stream())
+        L.check(rc, "floxb_ravel_codes")
+        self.launches += 1
+
+    def smem_group_limit(self, value_dtype, family: int) -> int:
+        return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))
+
+
+_backend = None
+
+
+def get_kernels():
+    """The active kernel backend.  CUDA unless a test installed an emulator via set_backend."""
+    global _backend
+    if _backend is None:
+        if not torch.cuda.is_available():
+            raise L.FloxB200Error("CUDA is not available and flox_b200 has no CPU fallback")
+        L.load()
+        _backend = CudaKernels()
+    return _backend
+
+
+def set_backend(backend) -> None:
+    """TEST HOOK: install an object implementing the CudaKernels interface (None restores CUDA)."""
+    global _backend
+    _backend = backend
+
+
+def default_device() -> torch.device:
+    k = get_kernels()
+    return torch.device("cuda", torch.cuda.current_device()) if k.name == "cuda" else torch.device("cpu")

@@ -1,0 +1,158 @@
+/* flox_b200 — C ABI of the B200 grouped-reduction engine.
+ *
+ * This is the drop-in boundary for flox's per-chunk hot path.  The reference has no FFI (it is
+ * pure Python); its plug-in seam is the *engine function contract*
+ *     f(group_idx, array, *, axis=-1, size=None, fill_value=None, dtype=None, **kw) -> ndarray
+ * resolved by name in flox/aggregations.py:85-90 (generic_aggregate) and called from
+ * flox/core.py:368-370 (chunk_reduce).  Each entry point below cites the reference function(s)
+ * it replaces.  A maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as host;
+ *   - no entry point allocates or synchronises; work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*, NULL = the legacy default stream);
+ *   - return value: 0 on success, negative FLOXB_E* otherwise (floxb_strerror gives text);
+ *   - a chunk is values[A, n, B] (C-contiguous) + codes[n]; codes outside [0, n_groups) are
+ *     skipped (flox/factorize.py:44-53,201-210 + flox/core.py:381-383 fused away);
+ *   - accumulators are [A, B, n_groups] and are WIDE: f64 for float inputs, i64 for integer
+ *     inputs, i64 counters.  Several calls may accumulate into the same buffers (init=0):
+ *     that is flox's _simple_combine (flox/dask.py:90-144) fused into the chunk kernel.
+ */
+#ifndef FLOX_B200_H_
+#define FLOX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLOXB_OK 0
+#define FLOXB_EINVAL (-1)  /* bad argument (null pointer, negative size, ...) */
+#define FLOXB_EDTYPE (-2)  /* unsupported dtype combination */
+#define FLOXB_ECUDA (-3)   /* a CUDA runtime call failed; see floxb_last_cuda_error() */
+#define FLOXB_ERANGE (-4)  /* size beyond what the kernels index */
+
+/* element types */
+#define FLOXB_F32 0
+#define FLOXB_F64 1
+#define FLOXB_I32 2
+#define FLOXB_I64 3
+
+/* floxb_moments op */
+#define FLOXB_OP_SUM 0   /* aggregate_flox.sum / nansum            (aggregate_flox.py:210-211) */
+#define FLOXB_OP_PROD 1  /* aggregate_flox.prod / nanprod          (aggregate_flox.py:212-213) */
+#define FLOXB_OP_SUMSQ 2 /* aggregate_flox.(nan)sum_of_squares     (aggregate_flox.py:225-244) */
+
+/* floxb_finalize kind */
+#define FLOXB_FIN_SUM 0     /* acc -> out; NaN-propagating unless skipna          */
+#define FLOXB_FIN_NANLEN 1  /* cnt -> out                      (aggregate_flox.py:247-248) */
+#define FLOXB_FIN_MEAN 2    /* acc/cnt                         (aggregate_flox.py:251-266) */
+#define FLOXB_FIN_MAX 3     /* key acc -> out                  (aggregate_flox.py:214-215) */
+#define FLOXB_FIN_MIN 4     /*                                 (aggregate_flox.py:216-217) */
+#define FLOXB_FIN_VAR 5     /* M2/(n-ddof)                     (aggregations.py:460-468)   */
+#define FLOXB_FIN_STD 6     /* sqrt of the above               (aggregations.py:471-472)   */
+#define FLOXB_FIN_ARG 7     /* index acc -> out, fill where no winner                       */
+#define FLOXB_FIN_COUNT_ALL 8 /* cnt+nnan -> out (rows with a valid label)                 */
+
+/* floxb_combine kind (flox/dask.py:131-143 with agg.simple_combine = np.sum/np.max/np.min) */
+#define FLOXB_COMB_SUM 0
+#define FLOXB_COMB_MAX 1
+#define FLOXB_COMB_MIN 2
+#define FLOXB_COMB_PROD 3
+#define FLOXB_COMB_NANMAX 4 /* np.nanmax: NaN blocks are skipped */
+#define FLOXB_COMB_NANMIN 5
+
+typedef struct floxb_chunk {
+  const void* values; /* device, [A, n, B] */
+  const void* codes;  /* device, [n] */
+  int64_t n;          /* length of the reduced axis in this chunk */
+} floxb_chunk_t;
+
+/* Library / build info. */
+int floxb_version(void);
+const char* floxb_strerror(int code);
+const char* floxb_last_cuda_error(void);
+/* Largest n_groups the shared-memory (privatised-bin) kernel path takes for this op family;
+ * above it the L2-atomic path is used.  Informational. */
+int64_t floxb_smem_group_limit(int value_dtype, int family /*0 moments, 1 minmax*/);
+
+/* Grouped sum / product / sum-of-squares plus non-NaN and NaN counts, one pass.
+ * Replaces aggregate_flox._np_grouped_op(op=np.add|multiply.reduceat) and nanlen
+ * (flox/aggregate_flox.py:133-192,195-217,225-248) and the sort in _prepare_for_flox
+ * (flox/aggregate_flox.py:9-23), which a scatter reduction does not need.
+ *   chunks     HOST array of n_chunks descriptors
+ *   acc        f64[A*B*G] for float values, i64[A*B*G] for integer values (non-NaN values only)
+ *   cnt, nnan  i64[A*B*G]: number of non-NaN / NaN values per group
+ *   init       1 = reset the accumulators first (0 / 1 for PROD), 0 = accumulate on top
+ *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics (testing / profiling) */
+int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
+                  int64_t A, int64_t B, int64_t n_groups, int op, void* acc, int64_t* cnt,
+                  int64_t* nnan, int init, int force_path, void* stream);
+
+/* Grouped max / min of the non-NaN values as order-preserving i64 keys, plus the counts.
+ * Replaces aggregate_flox.max/min/nanmax/nanmin (flox/aggregate_flox.py:214-217,195-207).
+ *   acc_key    i64[A*B*G]; init sets it to INT64_MIN (max) / INT64_MAX (min) */
+int floxb_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
+                 int64_t A, int64_t B, int64_t n_groups, int is_max, int64_t* acc_key,
+                 int64_t* cnt, int64_t* nnan, int init, int force_path, void* stream);
+
+/* Second pass of var_chunk: sum over rows of (x - mean[group])^2
+ * (flox/aggregations.py:375-387).  `means` is f64[A*B*G] (see floxb_group_means). */
+int floxb_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
+                int64_t A, int64_t B, int64_t n_groups, const double* means, int skipna,
+                double* acc_m2, int init, void* stream);
+
+/* means[g] = acc[g]/cnt[g], rounded through `value_dtype` like `array_sums / array_lens`
+ * (flox/aggregations.py:375-376); NaN when skipna==0 and the group saw a NaN. */
+int floxb_group_means(int value_dtype, const void* acc, const int64_t* cnt, const int64_t* nnan,
+                      int64_t n_bins, int skipna, double* means, void* stream);
+
+/* Position of the first extremum per group (numpy first-occurrence semantics; the reference
+ * pins them at tests/test_core.py:295,388-408; chunk_argreduce flox/core.py:157-211).
+ * Run floxb_minmax first; this pass finds, per group, the smallest `index_base + i` whose
+ * value equals the extremum (or is the first NaN when skipna==0 and the group has a NaN).
+ *   acc_idx    i64[A*B*G]; init sets INT64_MAX (= "no winner") */
+int floxb_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
+                 int64_t A, int64_t B, int64_t n_groups, const int64_t* acc_key,
+                 const int64_t* nnan, int skipna, const int64_t* index_base /*host, per chunk*/,
+                 int64_t* acc_idx, int init, void* stream);
+
+/* Typed result from wide accumulators: flox/core.py:410-475 (_finalize_results) pieces that
+ * are arithmetic — fill of absent groups (aggregate_flox.py:174-180), NaN propagation,
+ * mean = sum/count (aggregations.py:323-325), var = M2/(n-ddof) (aggregations.py:460-468),
+ * min_count masking (core.py:438-459).
+ *   acc        f64/i64 sums, i64 keys (MAX/MIN) or i64 indices (ARG); for VAR/STD the M2 (f64)
+ *   acc2       VAR/STD only: the f64 sum (unused otherwise, may be NULL)
+ *   out_dtype  FLOXB_* of `out`
+ *   fill_f/fill_i  value for groups with no rows (float / integer `out`)
+ *   min_count  >0: groups with cnt < min_count receive mc_fill_* instead (core.py:438-459)
+ *   ddof       VAR/STD only */
+int floxb_finalize(int kind, int value_dtype, int out_dtype, const void* acc, const void* acc2,
+                   const int64_t* cnt, const int64_t* nnan, int64_t n_bins, int skipna,
+                   double fill_f, int64_t fill_i, int64_t min_count, double mc_fill_f,
+                   int64_t mc_fill_i, int64_t ddof, void* out, void* stream);
+
+/* Reduce `nblk` stacked accumulator blocks [nblk, n_bins] into out[n_bins]
+ * (flox/dask.py:131-143).  dtype: FLOXB_F64 or FLOXB_I64. */
+int floxb_combine(int kind, int dtype, const void* stacked, int64_t nblk, int64_t n_bins,
+                  void* out, void* stream);
+
+/* Chan merge of stacked (M2, S, n) triples, each f64[nblk, n_bins] -> f64[n_bins]
+ * (flox/aggregations.py:392-451, _var_combine). */
+int floxb_var_combine(const double* m2, const double* s, const double* n, int64_t nblk,
+                      int64_t n_bins, double* out_m2, double* out_s, double* out_n, void* stream);
+
+/* Label encoding on device (flox/factorize.py:44-82).
+ *   floxb_digitize: codes[i] = bin index of labels[i] in `edges` (closed right or left), -1 when
+ *   outside or NaN — np.digitize + the pd.cut fix-up (factorize.py:55-82).  label_dtype F32/F64/I64.
+ *   floxb_ravel_codes: combined = c0*size1 + c1, -1 if either is -1 (factorize.py:102-108). */
+int floxb_digitize(const void* labels, int label_dtype, int64_t n, const double* edges,
+                   int64_t n_edges, int closed_right, int64_t* codes, void* stream);
+int floxb_ravel_codes(const int64_t* c0, const int64_t* c1, int64_t n, int64_t size0, int64_t size1,
+                      int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOX_B200_H_ */

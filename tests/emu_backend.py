@@ -1,0 +1,235 @@
+"""CPU emulator of the kernel layer — TEST INFRASTRUCTURE ONLY.
+
+Implements the `flox_b200.kernels.CudaKernels` interface with numpy on CPU torch tensors so that
+the package's HOST logic (dtype / fill rules, chunk driver, map-reduce plumbing, gloo world-size-2
+paths) can be tested on a machine without a GPU.  It restates what each `floxb_*` entry point of
+include/flox_b200.h promises; it is installed with `flox_b200.kernels.set_backend` by the CPU test
+fixtures and is never imported by the package.  GPU tests (`-m gpu`) never use it.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+F32, F64, I32, I64 = 0, 1, 2, 3
+INT64_MAX = np.iinfo(np.int64).max
+INT64_MIN = np.iinfo(np.int64).min
+
+
+def _np(t):
+    return None if t is None else t.numpy()
+
+
+def _key_enc(v: np.ndarray) -> np.ndarray:
+    if v.dtype == np.float32:
+        b = v.view(np.int32)
+        return (b ^ ((b >> 31) & 0x7FFFFFFF)).astype(np.int64)
+    if v.dtype == np.float64:
+        b = v.view(np.int64)
+        return b ^ ((b >> 63) & 0x7FFFFFFFFFFFFFFF)
+    return v.astype(np.int64)
+
+
+def _key_dec(k: np.ndarray, dtype) -> np.ndarray:
+    if dtype == np.float32:
+        b = k.astype(np.int32)
+        return (b ^ ((b >> 31) & 0x7FFFFFFF)).view(np.float32)
+    if dtype == np.float64:
+        return (k ^ ((k >> 63) & 0x7FFFFFFFFFFFFFFF)).view(np.float64)
+    return k.astype(dtype)
+
+
+class EmuKernels:
+    name = "emu"
+
+    def __init__(self):
+        self.launches = 0
+
+    def _iter(self, chunks, A, B, G):
+        """Yield (values[A,n,B] float64-or-int64 view, valid mask, bins[A,n,B]) per chunk."""
+        for v, c in chunks:
+            n = c.numel()
+            vals = v.numpy().reshape(A, n, B)
+            codes = c.numpy().astype(np.int64)
+            ok = (codes >= 0) & (codes < G)
+            bins = (np.arange(A)[:, None, None] * B + np.arange(B)[None, None, :]) * G + np.where(ok, codes, 0)[None, :, None]
+            valid = np.broadcast_to(ok[None, :, None], vals.shape)
+            yield vals, valid, bins
+
+    def moments(self, chunks, A, B, G, op, acc, cnt, nnan, init=True, force_path=0):
+        self.launches += 1
+        a, c, m = _np(acc), _np(cnt), _np(nnan)
+        if init:
+            a[...] = 1 if op == 1 else 0
+            c[...] = 0
+            m[...] = 0
+        for vals, valid, bins in self._iter(chunks, A, B, G):
+            isn = np.isnan(vals) if vals.dtype.kind == "f" else np.zeros(vals.shape, bool)
+            good = valid & ~isn
+            w = vals[good].astype(a.dtype)
+            if op == 2:
+                w = w * w
+            if op == 1:
+                np.multiply.at(a, bins[good], w)
+            else:
+                np.add.at(a, bins[good], w)
+            np.add.at(c, bins[good], 1)
+            np.add.at(m, bins[valid & isn], 1)
+
+    def minmax(self, chunks, A, B, G, is_max, key, cnt, nnan, init=True, force_path=0, value_dtype=None):
+        self.launches += 1
+        k, c, m = _np(key), _np(cnt), _np(nnan)
+        if init:
+            k[...] = INT64_MIN if is_max else INT64_MAX
+            c[...] = 0
+            m[...] = 0
+        for vals, valid, bins in self._iter(chunks, A, B, G):
+            isn = np.isnan(vals) if vals.dtype.kind == "f" else np.zeros(vals.shape, bool)
+            good = valid & ~isn
+            keys = _key_enc(np.ascontiguousarray(vals[good]))
+            (np.maximum if is_max else np.minimum).at(k, bins[good], keys)
+            np.add.at(c, bins[good], 1)
+            np.add.at(m, bins[valid & isn], 1)
+
+    def group_means(self, value_dtype, acc, cnt, nnan, skipna, means):
+        self.launches += 1
+        a, c, m, out = _np(acc), _np(cnt), _np(nnan), _np(means)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            if value_dtype == torch.float32:
+                mu = (a.astype(np.float32).astype(np.float64) / c).astype(np.float32).astype(np.float64)
+            else:
+                mu = a.astype(np.float64) / c
+        if not skipna:
+            mu = np.where(m > 0, np.nan, mu)
+        out[...] = mu
+
+    def sqdev(self, chunks, A, B, G, means, skipna, m2, init=True, value_dtype=None):
+        self.launches += 1
+        mu, out = _np(means), _np(m2)
+        if init:
+            out[...] = 0
+        for vals, valid, bins in self._iter(chunks, A, B, G):
+            isn = np.isnan(vals) if vals.dtype.kind == "f" else np.zeros(vals.shape, bool)
+            sel = valid & ~isn if skipna else valid
+            d = vals[sel].astype(np.float64) - mu[bins[sel]]
+            np.add.at(out, bins[sel], d * d)
+
+    def argext(self, chunks, A, B, G, key, nnan, skipna, index_base, idx, init=True, value_dtype=None):
+        self.launches += 1
+        k, m, out = _np(key), _np(nnan), _np(idx)
+        if init:
+            out[...] = INT64_MAX
+        for (vals, valid, bins), base in zip(self._iter(chunks, A, B, G), index_base):
+            n = vals.shape[1]
+            pos = np.broadcast_to((base + np.arange(n))[None, :, None], vals.shape)
+            isn = np.isnan(vals) if vals.dtype.kind == "f" else np.zeros(vals.shape, bool)
+            keys = _key_enc(np.ascontiguousarray(np.where(isn, 0, vals).astype(vals.dtype)))
+            poisoned = (m[bins] > 0) & (not skipna)
+            hit = valid & np.where(poisoned, isn, (~isn) & (keys == k[bins]))
+            np.minimum.at(out, bins[hit], pos[hit])
+
+    def finalize(self, kind, value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out):
+        self.launches += 1
+        o = _np(out)
+        c = _np(cnt).astype(np.int64)
+        m = _np(nnan).astype(np.int64) if nnan is not None else np.zeros_like(c)
+        rows = c + m
+        odt = o.dtype
+        is_f = odt.kind == "f"
+
+        def conv(v):
+            if v is None:
+                return np.array(np.nan if is_f else 0).astype(odt)
+            if not is_f:
+                try:
+                    return np.array(int(v)).astype(odt)
+                except (ValueError, OverflowError):
+                    return np.array(0, dtype=odt)
+            return np.array(float(v)).astype(odt)
+
+        fillv, mcv = conv(fill), conv(mc_fill)
+        nan = np.array(np.nan).astype(odt) if is_f else np.array(0, dtype=odt)
+        poisoned = (m > 0) & (not skipna)
+        with np.errstate(all="ignore"):
+            if kind == 0:  # SUM
+                r = np.where(rows == 0, fillv, np.where(poisoned, nan, _np(acc).astype(odt)))
+            elif kind == 1:  # NANLEN
+                r = np.where(rows == 0, fillv, c.astype(odt))
+            elif kind == 8:  # COUNT_ALL
+                r = rows.astype(odt)
+            elif kind == 2:  # MEAN
+                a = _np(acc)
+                s = a.astype(np.float32).astype(np.float64) if odt == np.float32 else a.astype(np.float64)
+                s = np.where(rows == 0, np.float64(fillv), np.where(poisoned, np.nan, s))
+                r = (s / c.astype(np.float64)).astype(odt)
+            elif kind in (3, 4):  # MAX / MIN
+                vdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[value_dtype]
+                v = _key_dec(_np(acc), vdt)
+                r = v.astype(odt)
+                if np.dtype(vdt).kind == "f" and skipna:
+                    ident = -np.inf if kind == 3 else np.inf
+                    r = np.where(v == ident, fillv, r)
+                r = np.where(c == 0, fillv, r)
+                r = np.where(poisoned, nan, r)
+                r = np.where(rows == 0, fillv, r)
+            elif kind in (5, 6):  # VAR / STD
+                den = (c - ddof).astype(np.float64)
+                v = np.where(poisoned, np.nan, _np(acc) / den)
+                v = np.where(den < 0, np.nan, v)
+                if kind == 6:
+                    v = np.sqrt(v)
+                r = v.astype(odt)
+            elif kind == 7:  # ARG
+                ix = _np(acc)
+                r = np.where(ix == INT64_MAX, fillv, ix.astype(odt))
+            else:
+                raise ValueError(kind)
+        if min_count > 0:
+            r = np.where(c < min_count, mcv, r)
+        o[...] = r.astype(odt)
+
+    def combine(self, kind, stacked, out):
+        self.launches += 1
+        s = _np(stacked)
+        with np.errstate(all="ignore"):
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                fn = {0: np.sum, 1: np.max, 2: np.min, 3: np.prod, 4: np.nanmax, 5: np.nanmin}[kind]
+                _np(out)[...] = fn(s, axis=0)
+
+    def var_combine(self, m2, s, n, out_m2, out_s, out_n):
+        self.launches += 1
+        M2, S, N = _np(m2), _np(s), _np(n)
+        m, ss, nn = M2[0].copy(), S[0].copy(), N[0].copy()
+        adj = np.zeros_like(m)
+        with np.errstate(all="ignore"):
+            for k in range(1, M2.shape[0]):
+                deg = (nn == 0) | (N[k] == 0)
+                num = nn * S[k] - N[k] * ss
+                adj = adj + num * num / (nn * N[k] * (nn + N[k]) + deg.astype(np.float64))
+                m, ss, nn = m + M2[k], ss + S[k], nn + N[k]
+        _np(out_m2)[...] = m + adj
+        _np(out_s)[...] = ss
+        _np(out_n)[...] = nn
+
+    def digitize(self, labels, edges, closed_right, codes):
+        self.launches += 1
+        x = _np(labels).astype(np.float64)
+        e = _np(edges)
+        if e.size < 2:
+            _np(codes)[...] = -1
+            return
+        idx = np.digitize(x, e, right=bool(closed_right)) - 1
+        inside = (x > e[0]) & (x <= e[-1]) if closed_right else (x >= e[0]) & (x < e[-1])
+        _np(codes)[...] = np.where(inside, idx, -1)
+
+    def ravel_codes(self, c0, c1, size0, size1, out):
+        self.launches += 1
+        a, b = _np(c0), _np(c1)
+        bad = (a < 0) | (b < 0) | (a >= size0) | (b >= size1)
+        _np(out)[...] = np.where(bad, -1, a * size1 + b)
+
+    def smem_group_limit(self, value_dtype, family):
+        return 14000
