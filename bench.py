@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — grouped rows/s of the flox hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): 1-D float32, 1e9 rows in 100 chunks of 1e7, int64 labels,
+1e4 random groups, func="mean", method="map-reduce".  One "step" = one full groupby_reduce over
+those 1e9 rows on each GPU (weak scaling: every rank holds its own 1e9 rows; ranks merge the
+[G] accumulators with an NCCL all-reduce inside the step).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference algorithm (oracle port) on host cores
+
+One JSON line on rank 0:  value = rows/s with inputs resident in HBM (CUDA events, max over ranks);
+e2e = the same through the public API with pinned HOST buffers (H2D + D2H inside the timed
+region); roofline = achieved GB/s of the dominant kernel (12 algorithmic bytes per row) over the
+measured HBM peak; cpu_baseline = the oracle (numpy restatement of engine="flox": stable argsort +
+reduceat) timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "grouped rows/sec + %HBM-roofline, 1e9×f32 sum by 1e4 groups @1/2/4/8 GPU vs CPU ref"
+UNIT = "rows/s"
+ROWS, CHUNK, NGROUPS, FUNC = 1_000_000_000, 10_000_000, 10_000, "mean"
+BYTES_PER_ROW = 12  # f32 value + i64 label, each read once
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--rows", type=int, default=ROWS, help="rows per GPU (default: the BASELINE config)")
+    p.add_argument("--chunk", type=int, default=CHUNK)
+    p.add_argument("--groups", type=int, default=NGROUPS)
+    p.add_argument("--func", default=FUNC)
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=20.0)
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm) — the only place bench.py executes oracle/
+# --------------------------------------------------------------------------------------------
+
+def cpu_chunks(nchunks: int, chunk: int, ngroups: int, seed: int = 12345):
+    rng = np.random.default_rng(seed)
+    return [(rng.random(chunk, dtype=np.float32), rng.integers(0, ngroups, chunk)) for _ in range(nchunks)]
+
+
+def cpu_mapreduce(chunks, ngroups: int, func: str, threads: int):
+    """flox's map-reduce restated on the CPU: per-chunk chunk_reduce (stable argsort + reduceat,
+    engine="flox"), simple_combine, finalize — one chunk per worker thread (numpy's sort and
+    reduceat release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import flox_oracle as O
+
+    agg = O.initialize(func, None, np.dtype("float32"), None, 0)
+    agg.fill["user"] = agg.fill["final"]
+
+    def one(c):
+        return O.chunk_reduce(c[0], c[1], agg.chunk, ngroups=ngroups, fills=agg.fill["intermediate"],
+                              dtypes=agg.dtype["intermediate"])
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        per_chunk = list(ex.map(one, chunks))
+    return O.finalize(O.simple_combine(per_chunk, agg), agg, do_finalize=True)
+
+
+def time_cpu(args, budget_s: float):
+    """rows/s of the reference algorithm on all host cores, bounded to ~budget_s seconds."""
+    threads = os.cpu_count() or 1
+    chunk = min(args.chunk, args.rows)
+    chunks = cpu_chunks(threads, chunk, args.groups)
+    t0 = time.perf_counter()
+    cpu_mapreduce(chunks[: max(1, threads // 4)], args.groups, args.func, threads)  # warm-up + cost probe
+    probe = (time.perf_counter() - t0)
+    rounds = max(1, min(5, int(budget_s / max(probe * 1.5, 1e-3))))
+    best = None
+    for _ in range(rounds):
+        t0 = time.perf_counter()
+        cpu_mapreduce(chunks, args.groups, args.func, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    rows = threads * chunk
+    return dict(value=rows / best, unit=UNIT, cores=threads, kind="port",
+                sample=f"{threads} chunks x {chunk} rows of the same workload (one chunk per host thread), best of {rounds}; "
+                       f"oracle port of engine='flox' (stable argsort + reduceat) + simple_combine + finalize"), rows, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    chunk = min(args.chunk, args.rows)
+    chunks = cpu_chunks(threads, chunk, args.groups)
+    for _ in range(min(args.warmup, 1)):
+        cpu_mapreduce(chunks, args.groups, args.func, threads)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_mapreduce(chunks, args.groups, args.func, threads)
+    dt = (time.perf_counter() - t0) / steps
+    rows = threads * chunk
+    value = rows / dt
+    sample = (f"each step = {threads} chunks x {chunk} rows (bounded sample of the 1e9-row workload, one chunk per host "
+              f"thread); {steps} timed steps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"1D float32 len={args.rows:.0e} chunked {chunk:.0e}, {args.groups} random groups, "
+                               f"func={args.func!r}, method='map-reduce' (CPU: engine='flox' algorithm, oracle port)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU legs
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes/launch of the dominant kernel from the committed ncu capture, if summarised."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import flox_b200
+    from flox_b200 import ChunkedArray, kernels, parallel
+    from flox_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    k = kernels.get_kernels()
+
+    rows, chunk, G = args.rows, min(args.chunk, args.rows), args.groups
+    gen = torch.Generator(device=dev).manual_seed(12345 + rank)
+    x = torch.rand(rows, device=dev, dtype=torch.float32, generator=gen)
+    by = torch.randint(0, G, (rows,), device=dev, dtype=torch.int64, generator=gen)
+    arr = ChunkedArray.from_array(x, chunk)
+    lab = ChunkedArray.from_array(by, chunk)
+    eg = np.arange(G)
+
+    def step():
+        with parallel.distributed(sharding="local"):
+            res, _ = flox_b200.groupby_reduce(arr, lab, func=args.func, expected_groups=eg, method="map-reduce")
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = k.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = k.kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * rows / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (roofline): floxb_moments over the same 100 chunks, CUDA events
+    chunks = [(v.reshape(1, -1, 1), c) for v, c in zip(arr.chunks, lab.chunks)]
+    acc = torch.empty(G, dtype=torch.float64, device=dev)
+    cnt = torch.empty(G, dtype=torch.int64, device=dev)
+    nnan = torch.empty(G, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        k.moments(chunks, 1, 1, G, L.OP_SUM, acc, cnt, nnan, init=False)
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 10))
+    kt = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        k.moments(chunks, 1, 1, G, L.OP_SUM, acc, cnt, nnan, init=False)
+        b.record()
+        b.synchronize()
+        kt.append(a.elapsed_time(b))
+    launches_per_call = -(-len(chunks) // 48)
+    kernel_ms = float(np.mean(kt)) / launches_per_call
+    peak, peak_src = hbm_peak()
+    achieved = BYTES_PER_ROW * (rows / launches_per_call) / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "k_moments_smem<float,long,SUM>", "peak_source": peak_src,
+                "kernel_ms_per_launch": kernel_ms, "launches_per_step": launches_per_call,
+                "algorithmic_bytes_per_launch": BYTES_PER_ROW * rows // launches_per_call}
+
+    # ---- end to end: pinned host buffers -> public API -> host result
+    e2e = None
+    if not args.no_e2e:
+        hx = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in arr.chunks]
+        hb = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in lab.chunks]
+        for h, d in zip(hx + hb, list(arr.chunks) + list(lab.chunks)):
+            h.copy_(d)
+        torch.cuda.synchronize()
+        del x, by, arr, lab, chunks
+        torch.cuda.empty_cache()
+        harr, hlab = ChunkedArray(hx), ChunkedArray(hb)
+
+        def e2e_step():
+            with parallel.distributed(sharding="local"):
+                r, _ = flox_b200.groupby_reduce(harr, hlab, func=args.func, expected_groups=eg, method="map-reduce")
+            return r.cpu() if isinstance(r, torch.Tensor) else r
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            out = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * rows / dt, "unit": UNIT, "h2d_bytes_per_step": world * rows * BYTES_PER_ROW,
+               "d2h_bytes_per_step": world * int(out.numel() * out.element_size()), "ms_per_step": dt * 1e3,
+               "steps": args.e2e_steps, "how": "pinned host chunks -> groupby_reduce(ChunkedArray, method='map-reduce') -> host result"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = time_cpu(args, args.cpu_seconds)
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"1D float32 len={rows:.0e} per GPU chunked {chunk:.0e}, {G} random int64-labelled groups, "
+                                   f"func={args.func!r}, method='map-reduce', engine='b200'",
+                       "accumulate": "f64 sums + i64 counts, rounded once to f32", "l2": "inputs (12 GB/GPU) >> 126 MB L2, no flush needed",
+                       "parallelism": f"dp{world}: rows sharded, [G] accumulators all-reduced (NCCL)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

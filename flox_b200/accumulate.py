@@ -20,7 +20,7 @@ from .kernels import acc_dtype, get_kernels
 
 class GroupedAccumulators:
     def __init__(self, chunks: Sequence[tuple[torch.Tensor, torch.Tensor]], A: int, B: int, G: int,
-                 value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None):
+                 value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None, comm=None):
         self.chunks = list(chunks)
         self.A, self.B, self.G = int(A), int(B), int(G)
         self.nbins = self.A * self.B * self.G
@@ -38,6 +38,9 @@ class GroupedAccumulators:
         self._var: dict[bool, tuple] = {}
         self._arg: dict[tuple, torch.Tensor] = {}
         self.k = get_kernels()
+        # cross-rank merge of every pass (parallel.Comm); None = single process.  Merging the
+        # raw accumulators right after each pass IS flox's combine stage (flox/dask.py:90-144).
+        self.comm = comm if (comm is not None and comm.enabled) else None
 
     # ---- allocation ----------------------------------------------------------------------
     def _i64(self):
@@ -64,6 +67,9 @@ class GroupedAccumulators:
             acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
             cnt, nnan = self._i64(), self._i64()
             self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
+            if self.comm:
+                (self.comm.prod_ if op == L.OP_PROD else self.comm.sum_)(acc)
+                self.comm.sum_(cnt, nnan)
             self._moments[(op, as_float)] = (acc, cnt, nnan)
         return self._moments[(op, as_float)]
 
@@ -72,6 +78,9 @@ class GroupedAccumulators:
             key, cnt, nnan = self._i64(), self._i64(), self._i64()
             self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
                           value_dtype=self.value_dtype)
+            if self.comm:
+                (self.comm.max_ if is_max else self.comm.min_)(key)
+                self.comm.sum_(cnt, nnan)
             self._minmax[is_max] = (key, cnt, nnan)
         return self._minmax[is_max]
 
@@ -91,7 +100,11 @@ class GroupedAccumulators:
             acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True)
             means, m2 = self._f64(), self._f64()
             self.k.group_means(vdt, acc, cnt, nnan, skipna, means)
+            # means come from the ALREADY MERGED sums, so M2 is about the global group mean and the
+            # cross-rank merge is a plain sum (no Chan adjustment terms needed, cf. aggregations.py:392-451)
             self.k.sqdev(chunks, self.A, self.B, self.G, means, skipna, m2, init=True, value_dtype=vdt)
+            if self.comm:
+                self.comm.sum_(m2)
             self._var[skipna] = (m2, acc, cnt, nnan)
         return self._var[skipna]
 
@@ -102,6 +115,8 @@ class GroupedAccumulators:
             idx = self._i64()
             self.k.argext(self.chunks, self.A, self.B, self.G, key, nnan, skipna, self.index_base, idx, init=True,
                           value_dtype=self.value_dtype)
+            if self.comm:  # key / nnan are already global, so local candidates are comparable
+                self.comm.min_(idx)
             self._arg[key_] = idx
         return self._arg[key_]
 

@@ -54,11 +54,36 @@ def _digitize_device(flat: torch.Tensor, edges: np.ndarray, right: bool) -> torc
     return codes
 
 
+def _is_int_index(expect) -> bool:
+    return (isinstance(expect, pd.Index) and not isinstance(expect, (pd.RangeIndex, pd.IntervalIndex))
+            and expect.dtype.kind in "iu" and len(expect) > 0 and expect.is_unique)
+
+
 def _factorize_single(by, expect, *, sort: bool, reindex: bool):
     """(groups Index, codes shaped like `by`) for one grouper (factorize.py:42-99)."""
     shape = tuple(by.shape)
     on_device = is_torch(by)
     flat = by.reshape(-1)
+    if on_device and not flat.dtype.is_floating_point and flat.dtype != torch.bool and _is_int_index(expect):
+        # integer labels against known integer groups, without leaving the device:
+        #  * groups == 0..G-1  -> the labels are the codes (kernels drop anything outside the range);
+        #  * otherwise         -> a lookup table over [min(groups), max(groups)] (the reference does a
+        #                         host searchsorted + isin here, factorize.py:84-94).
+        ex = np.asarray(expect, dtype=np.int64)
+        order = np.argsort(ex, kind="stable")
+        groups = expect[order] if sort else expect
+        lo, hi = int(ex.min()), int(ex.max())
+        if lo == 0 and hi == len(ex) - 1 and (sort or bool(np.all(order == np.arange(len(ex))))):
+            codes = flat if flat.dtype in (torch.int32, torch.int64) else flat.to(torch.int64)
+            return groups, codes.reshape(shape)
+        if hi - lo < (1 << 26):
+            table = np.full(hi - lo + 1, -1, dtype=np.int64)
+            table[(ex[order] if sort else ex) - lo] = np.arange(len(ex))
+            lut = torch.as_tensor(table, device=flat.device)
+            rel = flat.to(torch.int64) - lo
+            inside = (rel >= 0) & (rel <= hi - lo)
+            codes = torch.where(inside, lut[rel.clamp(0, hi - lo)], rel.new_full((), -1))
+            return groups, codes.reshape(shape)
     if isinstance(expect, pd.RangeIndex):
         # labels ARE codes; anything above the range is "no group".  The reference copies and
         # overwrites (factorize.py:44-53); the kernels' range check makes both unnecessary.

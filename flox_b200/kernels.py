@@ -10,6 +10,7 @@ tests/ (never imported by the package).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Sequence
 
 import torch
@@ -39,6 +40,30 @@ class CudaKernels:
 
     def __init__(self):
         self.launches = 0  # number of C-ABI kernel entry calls issued (bench reports it)
+        # testing / profiling knob: 1 = force the shared-memory path, 2 = force the L2-atomic path
+        self.force_path = int(os.environ.get("FLOXB_FORCE_PATH", "0"))
+        # CUDA kernel launches issued by the library (mirrors the launch logic of csrc/*.cu:
+        # optional fill kernel + one launch per <=48-chunk table on the shared-memory path, or one
+        # per non-empty chunk on the L2-atomic path).  bench.py reports it as `gpu_launches`.
+        self.kernel_launches = 0
+        self._limits: dict = {}
+
+    def _scan_launches(self, chunks, A, B, G, init, family, vdt, force_path, has_smem_path=True):
+        nbins = A * B * G
+        n = 1 if (init and nbins > 0) else 0
+        if nbins > 0:
+            nonempty = sum(1 for _, c in chunks if c.numel() > 0)
+            key = (vdt, family)
+            if key not in self._limits:
+                self._limits[key] = self.smem_group_limit(vdt, family)
+            smem = has_smem_path and A == 1 and B == 1 and G <= self._limits[key] and force_path != 2
+            if smem:
+                for lo in range(0, len(chunks), 48):
+                    if any(c.numel() > 0 for _, c in chunks[lo:lo + 48]):
+                        n += 1
+            else:
+                n += nonempty
+        self.kernel_launches += n
 
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
@@ -79,9 +104,11 @@ class CudaKernels:
         if vdt is None:
             vdt, cdt = (torch.float64 if acc.dtype == torch.float64 else torch.int64), torch.int64
         rc = L.load().floxb_moments(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, op, self._ptr(acc),
-                                    self._ptr(cnt), self._ptr(nnan), int(init), force_path, self._stream())
+                                    self._ptr(cnt), self._ptr(nnan), int(init), force_path or self.force_path,
+                                    self._stream())
         L.check(rc, "floxb_moments")
         self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 0, vdt, force_path or self.force_path)
 
     def minmax(self, chunks: Chunks, A: int, B: int, G: int, is_max: bool, key, cnt, nnan, init=True, force_path=0,
                value_dtype=None):
@@ -90,9 +117,11 @@ class CudaKernels:
         if vdt is None:
             vdt, cdt = value_dtype or torch.float64, torch.int64
         rc = L.load().floxb_minmax(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, int(is_max),
-                                   self._ptr(key), self._ptr(cnt), self._ptr(nnan), int(init), force_path, self._stream())
+                                   self._ptr(key), self._ptr(cnt), self._ptr(nnan), int(init),
+                                   force_path or self.force_path, self._stream())
         L.check(rc, "floxb_minmax")
         self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 1, vdt, force_path or self.force_path)
 
     def sqdev(self, chunks: Chunks, A: int, B: int, G: int, means, skipna: bool, m2, init=True, value_dtype=None):
         arr, vdt, cdt = self._chunk_array(chunks, A, B)
@@ -103,6 +132,7 @@ class CudaKernels:
                                   int(skipna), self._ptr(m2), int(init), self._stream())
         L.check(rc, "floxb_sqdev")
         self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 0, torch.float64, 0)
 
     def group_means(self, value_dtype, acc, cnt, nnan, skipna: bool, means):
         self._require_cuda(acc, cnt, nnan, means)
@@ -110,6 +140,7 @@ class CudaKernels:
                                         acc.numel(), int(skipna), self._ptr(means), self._stream())
         L.check(rc, "floxb_group_means")
         self.launches += 1
+        self.kernel_launches += 1
 
     def argext(self, chunks: Chunks, A: int, B: int, G: int, key, nnan, skipna: bool, index_base: Sequence[int], idx,
                init=True, value_dtype=None):
@@ -122,6 +153,7 @@ class CudaKernels:
                                    self._ptr(nnan), int(skipna), base, self._ptr(idx), int(init), self._stream())
         L.check(rc, "floxb_argext")
         self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 0, vdt, 0, has_smem_path=False)
 
     # -- epilogues -------------------------------------------------------------------------
     def finalize(self, kind: int, value_dtype, acc, acc2, cnt, nnan, skipna: bool, fill, min_count: int, mc_fill,
@@ -145,6 +177,7 @@ class CudaKernels:
                                      mi, int(ddof), self._ptr(out), self._stream())
         L.check(rc, "floxb_finalize")
         self.launches += 1
+        self.kernel_launches += 1
 
     def combine(self, kind: int, stacked, out):
         self._require_cuda(stacked, out)
@@ -153,6 +186,7 @@ class CudaKernels:
                                     self._stream())
         L.check(rc, "floxb_combine")
         self.launches += 1
+        self.kernel_launches += 1
 
     def var_combine(self, m2, s, n, out_m2, out_s, out_n):
         self._require_cuda(m2, s, n, out_m2, out_s, out_n)
@@ -160,6 +194,7 @@ class CudaKernels:
                                         self._ptr(out_m2), self._ptr(out_s), self._ptr(out_n), self._stream())
         L.check(rc, "floxb_var_combine")
         self.launches += 1
+        self.kernel_launches += 1
 
     # -- label encoding --------------------------------------------------------------------
     def digitize(self, labels, edges, closed_right: bool, codes):
@@ -168,6 +203,7 @@ class CudaKernels:
                                      edges.numel(), int(closed_right), self._ptr(codes), self._stream())
         L.check(rc, "floxb_digitize")
         self.launches += 1
+        self.kernel_launches += 1
 
     def ravel_codes(self, c0, c1, size0: int, size1: int, out):
         self._require_cuda(c0, c1, out)
@@ -175,6 +211,7 @@ class CudaKernels:
                                         self._stream())
         L.check(rc, "floxb_ravel_codes")
         self.launches += 1
+        self.kernel_launches += 1
 
     def smem_group_limit(self, value_dtype, family: int) -> int:
         return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))

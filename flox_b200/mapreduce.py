@@ -1,0 +1,166 @@
+"""Chunked (dask-like) inputs: map-reduce / blockwise / cohorts on the GPU(s).
+
+Replaces `dask_groupby_agg` + `_simple_combine` + `_aggregate` + `_expand_dims`
+(flox/dask.py:325-571, 90-175).  The reference builds a task graph: one `chunk_reduce` per block
+(dask.py:395-429), a tree of `_simple_combine` nodes (dask.py:440-460) and a final `_aggregate`.
+On a GPU the chunks owned by a rank stream through ONE persistent kernel launch into shared
+accumulators (chunk_reduce and the combine tree fuse), ranks merge accumulators with an
+all-reduce (parallel.py), and the reference's finalize semantics are applied to the merged result:
+
+* method="map-reduce": intermediates are evaluated with the INTERMEDIATE fills / dtypes
+  (aggregations.py:973-984), then `_finalize_results` runs agg.finalize and the min_count mask —
+  an absent group therefore finishes as e.g. 0 for `sum`, exactly like the reference's reindexed
+  map-reduce;
+* method="blockwise" / "cohorts": every group is completed by the blocks / cohort that hold it,
+  the result is the numpy-path value (dask.py:390-392,469-518) and absent groups get the final fill.
+
+`_simple_combine` / `_aggregate` / `_expand_dims` are also provided for explicit per-chunk
+intermediates (API parity and the golden tests).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import parallel
+from .accumulate import GroupedAccumulators
+from .aggregations import Aggregation, _is_arg_reduction, is_var_chunk_reduction, var_chunk
+from .arrays import from_device, is_torch, kernel_dtype, to_device
+from .chunked import ChunkedArray, is_chunked
+from .core import DUMMY_AXIS, _finalize_results
+from .kernels import default_device
+from .multiarray import MultiArray
+from .reductions import evaluate, var_triple
+from .reindex import ReindexStrategy
+
+
+# ---- explicit intermediates (reference-shaped API) ---------------------------------------------
+
+def _expand_dims(results: dict) -> dict:
+    """Insert DUMMY_AXIS into every intermediate (flox/dask.py:154-158)."""
+    def one(a):
+        if isinstance(a, MultiArray):
+            return MultiArray(tuple(one(x) for x in a.arrays))
+        return a.unsqueeze(DUMMY_AXIS) if is_torch(a) else np.expand_dims(a, DUMMY_AXIS)
+
+    results["intermediates"] = tuple(one(a) for a in results["intermediates"])
+    return results
+
+
+def _concat(parts, axis):
+    if isinstance(parts[0], MultiArray):
+        return MultiArray(tuple(_concat([p.arrays[i] for p in parts], axis) for i in range(len(parts[0].arrays))))
+    return torch.cat(list(parts), dim=axis) if is_torch(parts[0]) else np.concatenate(parts, axis=axis)
+
+
+def _simple_combine(x_chunk, agg: Aggregation, axis, keepdims: bool, reindex: ReindexStrategy | None = None,
+                    is_aggregate: bool = False) -> dict:
+    """Concatenate per-chunk intermediates on DUMMY_AXIS and reduce it (flox/dask.py:90-144).
+    `x_chunk`: list of chunk_reduce dicts already passed through `_expand_dims`."""
+    results = {"groups": x_chunk[0]["groups"], "intermediates": []}
+    for idx, combine in enumerate(agg.simple_combine):
+        if combine is None:
+            raise NotImplementedError("arg-reductions need the grouped (value, index) combine")
+        stacked = _concat([x["intermediates"][idx] for x in x_chunk], DUMMY_AXIS)
+        nd = stacked.ndim
+        result = combine(stacked, axis=(nd + DUMMY_AXIS,), keepdims=True)
+        if is_aggregate:
+            result = result.squeeze(nd + DUMMY_AXIS)
+        results["intermediates"].append(result)
+    return results
+
+
+def _aggregate(x_chunk, combine, agg: Aggregation, expected_groups, axis, keepdims: bool, fill_value, reindex) -> dict:
+    """Last node of the tree: combine, then finalize (flox/dask.py:161-175)."""
+    results = combine(x_chunk, agg, axis, keepdims, is_aggregate=True)
+    return _finalize_results(results, agg, axis, expected_groups, reindex=reindex)
+
+
+# ---- fused GPU path -------------------------------------------------------------------------------
+
+def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext):
+    """Device tensors `(values[A, n_k, 1], codes[n_k])` for the chunks this rank owns, plus the
+    global position of each chunk's first element along the reduced axis."""
+    device = default_device()
+    mine = ctx.my_chunks(array.nchunks)
+    sizes = array.chunk_sizes
+    if ctx.sharding == "local" and ctx.comm.enabled:
+        totals = ctx.comm.all_gather_object(sum(sizes))
+        start = sum(totals[: ctx.comm.rank])
+    else:
+        start = 0
+    offsets = np.concatenate([[0], np.cumsum(sizes)])[:-1] + start
+    by_chunks = by.rechunk_like(array).chunks if is_chunked(by) else None
+    lead = tuple(array.shape[:-1])
+    A = math.prod(lead)
+    kdt = kernel_dtype(to_device(array.chunks[0][..., :0], device).dtype) if array.nchunks else torch.float32
+    chunks, index_base = [], []
+    for k in mine:
+        v = to_device(array.chunks[k], device)
+        if v.dtype != kdt:
+            v = v.to(kdt)
+        if by_chunks is not None:
+            c = to_device(by_chunks[k], device)
+        else:
+            lo = int(offsets[k] - start)
+            c = to_device(by[..., lo:lo + sizes[k]], device)
+        if c.dtype not in (torch.int32, torch.int64):
+            c = c.to(torch.int64)
+        chunks.append((v.reshape(A, -1, 1), c.reshape(-1)))
+        index_base.append(int(offsets[k]))
+    return chunks, index_base, lead, A, kdt, device
+
+
+def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_groups: pd.RangeIndex, axis, fill_value,
+                        method: str, reindex: ReindexStrategy, engine: str, sort: bool = True):
+    """GPU counterpart of flox.dask.dask_groupby_agg (flox/dask.py:325-571).  `by` holds integer
+    codes against `expected_groups` (a RangeIndex) and is 1-D along the chunked axis."""
+    if by.ndim != 1:
+        raise NotImplementedError("chunked inputs are grouped by 1-D labels along the chunked (last) axis")
+    ctx = parallel.current()
+    G = len(expected_groups)
+    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx)
+    acc = GroupedAccumulators(chunks, A, 1, G, kdt, device, index_base=index_base, comm=ctx.comm)
+    like = array.chunks[0]
+    array_np_dtype = array.dtype
+    shape = lead + (G,)
+
+    def typed(t, dt):
+        return from_device(t.reshape(shape), like, dt)
+
+    if method == "map-reduce" and not _is_arg_reduction(agg):
+        funcs, fills, dts = agg.chunk, agg.fill_value["intermediate"], agg.dtype["intermediate"]
+        do_finalize = True
+    else:  # blockwise / cohorts / arg-reductions: straight to the numpy-path value
+        funcs, fills, dts = agg.numpy, agg.fill_value["numpy"], agg.dtype["numpy"]
+        do_finalize = False
+    ddof = agg.finalize_kwargs.get("ddof", 0) if agg.finalize_kwargs else 0
+
+    inter, previous = [], None
+    for red, fv, dt in zip(funcs, fills, dts):
+        if red == "nanlen" and previous == "nanlen":
+            inter.append(inter[-1])
+        elif is_var_chunk_reduction(red):
+            base, pkw = red.func, red.keywords
+            skipna = bool(pkw.get("skipna", False))
+            out_dt = np.dtype(dt) if dt is not None else (array_np_dtype if array_np_dtype.kind == "f" else np.dtype("float64"))
+            if base is var_chunk:
+                inter.append(MultiArray(tuple(typed(t, out_dt) for t in var_triple(acc, skipna, out_dt))))
+            else:
+                name = ("nan" if skipna else "") + ("std" if pkw.get("std", False) else "var")
+                inter.append(typed(evaluate(acc, name, out_dtype=out_dt, fill_value=np.nan, ddof=ddof), out_dt))
+        elif callable(red):
+            raise NotImplementedError("custom chunk callables are supported for in-memory arrays only")
+        else:
+            out_dt = np.dtype(dt) if dt is not None else array_np_dtype
+            inter.append(typed(evaluate(acc, red, out_dtype=out_dt, fill_value=fv), out_dt))
+        previous = red
+
+    if not do_finalize:
+        agg.finalize = None
+    results = {"groups": np.asarray(expected_groups), "intermediates": inter}
+    final = _finalize_results(results, agg, axis, expected_groups, reindex=ReindexStrategy(blockwise=True))
+    return final[agg.name], (final["groups"],)

@@ -1,0 +1,111 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch).
+
+flox's map-reduce has exactly one exchange step: the tree combine of per-chunk intermediates
+(`_tree_reduce(combine=_simple_combine)`, flox/dask.py:440-460; the scheduler moves python dicts).
+Here every rank accumulates ITS chunks into `[A, B, G]` wide accumulators and the combine is an
+all-reduce of those accumulators — sum for sums / counts, max / min for extremum keys and indices.
+The payload is tiny next to the inputs (G x 24 B at config 2), so the collective is latency-bound
+and NCCL's own algorithm choice (NVLS in-switch reduction when available) is what we want; there
+is no compute to overlap it with inside a chunk kernel.
+
+`Comm` wraps a process group; `LOCAL` (no group) turns every collective into a no-op so the same
+code runs single-GPU.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+class Comm:
+    """Collectives on accumulator tensors.  `group=None` + `world_size==1` -> no-ops."""
+
+    def __init__(self, group=None, enabled: bool | None = None):
+        self.group = group
+        if enabled is None:
+            enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.enabled = enabled
+        self.collectives = 0
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if self.enabled else 1
+
+    @property
+    def rank(self) -> int:
+        return dist.get_rank(self.group) if self.enabled else 0
+
+    def _reduce(self, t: torch.Tensor, op) -> torch.Tensor:
+        if self.enabled and t.numel():
+            dist.all_reduce(t, op=op, group=self.group)
+            self.collectives += 1
+        return t
+
+    def sum_(self, *tensors):
+        for t in tensors:
+            self._reduce(t, dist.ReduceOp.SUM)
+
+    def max_(self, t):
+        return self._reduce(t, dist.ReduceOp.MAX)
+
+    def min_(self, t):
+        return self._reduce(t, dist.ReduceOp.MIN)
+
+    def prod_(self, t):
+        return self._reduce(t, dist.ReduceOp.PRODUCT)
+
+    def all_gather_object(self, obj):
+        if not self.enabled:
+            return [obj]
+        out = [None] * self.world_size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
+LOCAL = Comm(enabled=False)
+
+
+@dataclass
+class ParallelContext:
+    """How chunked inputs map onto ranks.
+
+    sharding = "replicated": every rank was handed the same ChunkedArray and reduces the chunks
+                             `assignment(rank)` gives it (contiguous blocks by default, so sorted
+                             labels stay sorted per rank: the cohorts layout of SURVEY §8e);
+               "local":      the ChunkedArray a rank holds IS its shard.
+    """
+
+    comm: Comm = LOCAL
+    sharding: str = "replicated"
+
+    def my_chunks(self, nchunks: int) -> range:
+        if self.sharding == "local" or not self.comm.enabled:
+            return range(nchunks)
+        w, r = self.comm.world_size, self.comm.rank
+        base, extra = divmod(nchunks, w)
+        lo = r * base + min(r, extra)
+        return range(lo, lo + base + (1 if r < extra else 0))
+
+
+_current = ParallelContext()
+
+
+def current() -> ParallelContext:
+    return _current
+
+
+@contextlib.contextmanager
+def distributed(group=None, sharding: str = "replicated"):
+    """Run `groupby_reduce` on ChunkedArrays across the ranks of `group` (default: WORLD)."""
+    global _current
+    if sharding not in ("replicated", "local"):
+        raise ValueError("sharding must be 'replicated' or 'local'")
+    prev = _current
+    _current = ParallelContext(Comm(group), sharding)
+    try:
+        yield _current
+    finally:
+        _current = prev

@@ -1,0 +1,205 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the reference-made golden
+vectors and against the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu.
+
+Bars (BASELINE.json north_star): bit-exact for count / nanlen / argmin / argmax and every integer
+result; within 1e-6 relative for float sum / mean / var on f32 inputs (1e-12 on f64 inputs), with
+an absolute slack of the same factor times the magnitude of the summands for sums that cancel
+(tests/golden_io.py:cond_atol).
+"""
+import numpy as np
+import pytest
+import torch
+
+import flox_b200
+from flox_b200 import ChunkedArray, kernels
+from oracle import flox_oracle as O
+from tests.golden_io import api_kwargs, assert_same, cond_atol, load_golden
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden()
+RTOL32, RTOL64 = 1e-6, 1e-12
+
+
+@pytest.fixture(autouse=True)
+def _cuda_backend():
+    assert torch.cuda.is_available(), "GPU tests need CUDA"
+    kernels.set_backend(None)
+    k = kernels.get_kernels()
+    assert k.name == "cuda"
+    k.force_path = 0
+    yield k
+    k.force_path = 0
+
+
+def _ids(cases):
+    return [c["id"] for c in cases]
+
+
+def _tols(func, arr, prec=False):
+    r64 = RTOL32 if arr.dtype == np.float32 else RTOL64
+    if prec:
+        r64 = 3e-8  # the reference's own tolerance for the 1e12-offset cases (tests/test_core.py:2287-2319)
+    return dict(rtol_f32=RTOL32, rtol_f64=r64, atol_f32=cond_atol(func, arr, RTOL32), atol_f64=cond_atol(func, arr, r64))
+
+
+# ---- golden vectors -----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", G.family("api"), ids=_ids(G.family("api")))
+def test_api_golden(case):
+    kw = api_kwargs(case)
+    fk = {"ddof": case["ddof"]} if case["ddof"] else None
+    bys = [G.arr(b) for b in case["bys"]]
+    arr = G.arr(case["array"])
+    if "raises" in case:
+        if case["func"].startswith(("arg", "nanarg")):
+            pytest.skip("engine='flox' rejects arg-reductions; b200 implements them (test_arg_reductions)")
+        with pytest.raises(Exception):
+            flox_b200.groupby_reduce(arr, *bys, func=case["func"], finalize_kwargs=fk, **kw)
+        return
+    res, *groups = flox_b200.groupby_reduce(arr, *bys, func=case["func"], finalize_kwargs=fk, **kw)
+    assert_same(res, G.arr(case["result"]), what=case["id"], **_tols(case["func"], arr, case["id"].startswith("api/prec")))
+    for g, key in zip(groups, case["groups"]):
+        g = np.asarray(g)
+        if g.dtype == object and len(g) and hasattr(g[0], "left"):
+            g = np.asarray([iv.left for iv in g] + [g[-1].right])
+        np.testing.assert_array_equal(g, G.arr(key))
+
+
+@pytest.mark.parametrize("path", [1, 2], ids=["smem", "l2"])
+@pytest.mark.parametrize("case", G.family("engine"), ids=_ids(G.family("engine")))
+def test_engine_golden(case, path, _cuda_backend):
+    """aggregate_b200.<func>(codes, array, size=, fill_value=, dtype=) on BOTH kernel paths."""
+    arr = G.arr(case["array"])
+    if path == 1 and arr.ndim > 1 and arr.shape[0] > 1:
+        path = 0  # the shared-memory path takes 1-D problems; let the dispatcher choose
+    _cuda_backend.force_path = path
+    fn = getattr(flox_b200.aggregate_b200, case["func"])
+    dt = None if case["dtype"] is None else np.dtype(case["dtype"])
+    res = fn(G.arr(case["codes"]), arr, size=case["size"], fill_value=case["fill_value"], dtype=dt)
+    want = G.arr(case["result"])
+    if case["func"] == "nanlen":
+        res = res.astype(want.dtype)
+    assert_same(res, want, what=case["id"], **_tols(case["func"], arr))
+
+
+@pytest.mark.parametrize("case", G.family("mapred"), ids=_ids(G.family("mapred")))
+def test_mapreduce_golden(case):
+    a, by = G.arr(case["array"]), G.arr(case["by"])
+    bounds = np.linspace(0, a.shape[-1], case["nchunks"] + 1).astype(int)
+    arr = ChunkedArray([a[..., lo:hi] for lo, hi in zip(bounds[:-1], bounds[1:])])
+    kw = dict(expected_groups=np.arange(case["ngroups"]), fill_value=case["fill_value"], method="map-reduce")
+    if case["dtype"] is not None:
+        kw["dtype"] = np.dtype(case["dtype"])
+    if case["min_count"]:
+        kw["min_count"] = case["min_count"]
+    if case["ddof"]:
+        kw["finalize_kwargs"] = {"ddof": case["ddof"]}
+    res, _ = flox_b200.groupby_reduce(arr, by, func=case["func"], **kw)
+    assert_same(res, G.arr(case["result"]), what=case["id"], **_tols(case["func"], a))
+
+
+# ---- seeded problems against the oracle ------------------------------------------------------------
+
+FUNCS = ["count", "sum", "nansum", "mean", "nanmean", "var", "nanvar", "nanstd", "max", "nanmax", "min", "nanmin"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("N,ngroups", [(1_000_003, 100), (2_000_000, 10_000), (500_000, 40_000), (65_537, 1)])
+def test_seeded_vs_oracle(N, ngroups, dtype):
+    """Sizes the oracle finishes in seconds; 40k groups exercises the L2-atomic path, 1e4 the
+    shared-memory path with the exact headline shape, odd N the unaligned tails."""
+    rng = np.random.default_rng(12345)
+    by = rng.integers(0, ngroups, N)
+    if ngroups > 2:
+        by[by == 1] = 2       # an absent group
+        by[::1001] = -1       # "no group" codes (NaN labels after factorization)
+    if np.dtype(dtype).kind == "f":
+        x = (rng.random(N) * 4 - 1).astype(dtype)
+        x[rng.random(N) < 0.01] = np.nan
+    else:
+        x = rng.integers(-1000, 1000, N).astype(dtype)
+    for func in FUNCS:
+        fk = {"ddof": 1} if func in ("var", "nanvar") else None
+        kw = dict(expected_groups=np.arange(ngroups))
+        got, _ = flox_b200.groupby_reduce(x, by, func=func, finalize_kwargs=fk, **kw)
+        want, _ = O.groupby_reduce(x, by, func=func, ddof=1 if fk else 0, **kw)
+        assert_same(got, want, what=f"{func}/{np.dtype(dtype)}/{N}/{ngroups}", **_tols(func, x))
+
+
+@pytest.mark.parametrize("func", ["argmax", "argmin", "nanargmax", "nanargmin"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+def test_arg_reductions(func, dtype):
+    """First-occurrence semantics, bit-exact (reference pins numpy's: tests/test_core.py:388-408)."""
+    rng = np.random.default_rng(7)
+    N, ngroups = 50_000, 37
+    by = rng.integers(0, ngroups, N)
+    by[by == 3] = 4
+    x = rng.integers(0, 50, N).astype(dtype)  # many ties
+    if np.dtype(dtype).kind == "f":
+        x[rng.random(N) < 0.02] = np.nan
+        x[by == 7] = np.nan  # an all-NaN group
+    got, _ = flox_b200.groupby_reduce(x, by, func=func, expected_groups=np.arange(ngroups))
+    want, _ = O.groupby_reduce(x, by, func=func, expected_groups=np.arange(ngroups))
+    assert got.dtype == want.dtype
+    np.testing.assert_array_equal(got, want)
+
+
+def test_multidim_layouts_vs_oracle():
+    """(A, n) row-batched arrays, axis-subset reductions with 2-D labels, broadcast labels."""
+    rng = np.random.default_rng(99)
+    arr = rng.random((6, 5, 4000)).astype(np.float32)
+    arr[0, 0, ::7] = np.nan
+    by1 = rng.integers(0, 12, 4000)
+    by2 = rng.integers(0, 12, (5, 4000))
+    for func in ("sum", "nanmean", "max", "count", "nanvar"):
+        for by, kw in ((by1, {}), (by2, {}), (by2, dict(axis=-1)), (by1.reshape(1, -1), {})):
+            kw = dict(kw, expected_groups=np.arange(12))
+            got, _ = flox_b200.groupby_reduce(arr, by, func=func, **kw)
+            want, _ = O.groupby_reduce(arr, by, func=func, **kw)
+            assert_same(got, want, what=f"{func}/{by.shape}/{kw}", **_tols(func, arr))
+
+
+def test_torch_cuda_inputs_stay_on_device():
+    rng = np.random.default_rng(5)
+    x = rng.random(300_000).astype(np.float32)
+    by = rng.integers(0, 500, 300_000)
+    xt, bt = torch.as_tensor(x, device="cuda"), torch.as_tensor(by, device="cuda")
+    got, groups = flox_b200.groupby_reduce(xt, bt, func="nanmean", expected_groups=np.arange(500))
+    assert isinstance(got, torch.Tensor) and got.is_cuda and got.dtype == torch.float32
+    want, _ = O.groupby_reduce(x, by, func="nanmean", expected_groups=np.arange(500))
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-6)
+
+
+# ---- size-independent properties at (near) full size -----------------------------------------------
+
+def test_full_size_properties():
+    """2.5e8 f32 rows x 1e4 groups generated on device (3 GB): totals conserve, chunking and the
+    kernel path do not change the answer, counts are exact."""
+    gen = torch.Generator(device="cuda").manual_seed(12345)
+    N, ngroups = 250_000_000, 10_000
+    x = torch.rand(N, device="cuda", generator=gen, dtype=torch.float32)
+    by = torch.randint(0, ngroups, (N,), device="cuda", generator=gen, dtype=torch.int64)
+    eg = np.arange(ngroups)
+    s, _ = flox_b200.groupby_reduce(x, by, func="sum", expected_groups=eg, dtype=np.float64)
+    c, _ = flox_b200.groupby_reduce(x, by, func="count", expected_groups=eg)
+    assert int(c.sum()) == N
+    torch.testing.assert_close(c, torch.bincount(by, minlength=ngroups), rtol=0, atol=0)
+    total = x.to(torch.float64).sum()
+    assert abs(float(s.sum() - total)) <= 1e-9 * float(total)
+    # chunked map-reduce == single shot (f64 accumulators: identical up to atomics order)
+    sm, _ = flox_b200.groupby_reduce(ChunkedArray.from_array(x, 10_000_000), by, func="sum", expected_groups=eg,
+                                     dtype=np.float64, method="map-reduce")
+    torch.testing.assert_close(sm, s, rtol=1e-12, atol=0)
+    # L2-atomic path == shared-memory path
+    k = kernels.get_kernels()
+    k.force_path = 2
+    s2, _ = flox_b200.groupby_reduce(x[: N // 10], by[: N // 10], func="sum", expected_groups=eg, dtype=np.float64)
+    k.force_path = 0
+    s1, _ = flox_b200.groupby_reduce(x[: N // 10], by[: N // 10], func="sum", expected_groups=eg, dtype=np.float64)
+    torch.testing.assert_close(s2, s1, rtol=1e-12, atol=0)
+    # max over groups == global max; mean within f32 of sum/count
+    mx, _ = flox_b200.groupby_reduce(x, by, func="max", expected_groups=eg)
+    assert float(mx.max()) == float(x.max())
+    mean, _ = flox_b200.groupby_reduce(x, by, func="mean", expected_groups=eg)
+    torch.testing.assert_close(mean.to(torch.float64), s / c, rtol=2e-7, atol=0)
