@@ -1,6 +1,6 @@
 """flox_b200 — B200-native grouped reductions behind flox's `groupby_reduce` / `Aggregation` /
 engine plug-in contract.  See DESIGN.md; the C ABI is include/flox_b200.h."""
-from . import aggregate_b200  # noqa: F401
+from . import aggregate_b200, parallel  # noqa: F401
 from .aggregations import Aggregation, generic_aggregate  # noqa: F401
 from .chunked import ChunkedArray  # noqa: F401
 from .core import chunk_reduce, groupby_reduce  # noqa: F401

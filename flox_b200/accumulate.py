@@ -34,6 +34,7 @@ class GroupedAccumulators:
         self.index_base = list(index_base)
         self._moments: dict[tuple, tuple] = {}
         self._fchunks = None
+        self._gindex: dict[int, tuple] = {}
         self._minmax: dict[bool, tuple] = {}
         self._var: dict[bool, tuple] = {}
         self._arg: dict[tuple, torch.Tensor] = {}
@@ -59,6 +60,33 @@ class GroupedAccumulators:
             self._fchunks = [(v.to(torch.float64), c) for v, c in self.chunks]
         return self._fchunks, torch.float64
 
+    # ---- column-owner path (kept trailing dims, B > 1) ------------------------------------------
+    COLS_MIN_COLUMNS = 32768  # enough independent columns to fill 148 SMs with 16-byte loads
+
+    def _use_cols(self) -> bool:
+        return (self.B > 1 and self.A * self.B >= self.COLS_MIN_COLUMNS and self.A <= 65535 and self.nbins > 0
+                and any(c.numel() for _, c in self.chunks))
+
+    def _group_index(self, k: int):
+        """(perm, goff) of chunk k: rows grouped by code (one counting sort over the LABELS only)."""
+        if k not in self._gindex:
+            codes = self.chunks[k][1]
+            perm = torch.empty(codes.numel(), dtype=torch.int64, device=self.device)
+            goff = torch.empty(self.G + 1, dtype=torch.int64, device=self.device)
+            cursor = torch.empty(max(self.G, 1), dtype=torch.int64, device=self.device)
+            self.k.group_index(codes, self.G, perm, goff, cursor)
+            self._gindex[k] = (perm, goff)
+        return self._gindex[k]
+
+    def _reduce_cols(self, chunks, mode: int, acc, cnt, nnan):
+        first = True
+        for k, (v, c) in enumerate(chunks):
+            if c.numel() == 0:
+                continue
+            perm, goff = self._group_index(k)
+            self.k.reduce_cols(v, perm, goff, self.A, c.numel(), self.B, self.G, mode, acc, cnt, nnan, init=first)
+            first = False
+
     def moments(self, op: int = L.OP_SUM, as_float: bool = False):
         """(acc, cnt, nnan): acc = op over non-NaN values, cnt/nnan = # non-NaN / NaN values."""
         as_float = bool(as_float) and not self.value_dtype.is_floating_point
@@ -66,7 +94,10 @@ class GroupedAccumulators:
             chunks, vdt = self._chunks_as(as_float)
             acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
             cnt, nnan = self._i64(), self._i64()
-            self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
+            if self._use_cols():
+                self._reduce_cols(chunks, op, acc, cnt, nnan)
+            else:
+                self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
             if self.comm:
                 (self.comm.prod_ if op == L.OP_PROD else self.comm.sum_)(acc)
                 self.comm.sum_(cnt, nnan)
@@ -76,8 +107,11 @@ class GroupedAccumulators:
     def minmax(self, is_max: bool):
         if is_max not in self._minmax:
             key, cnt, nnan = self._i64(), self._i64(), self._i64()
-            self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
-                          value_dtype=self.value_dtype)
+            if self._use_cols():
+                self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan)
+            else:
+                self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
+                              value_dtype=self.value_dtype)
             if self.comm:
                 (self.comm.max_ if is_max else self.comm.min_)(key)
                 self.comm.sum_(cnt, nnan)

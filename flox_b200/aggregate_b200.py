@@ -44,15 +44,32 @@ def make_accumulators(group_idx, array, size=None) -> tuple[GroupedAccumulators,
     """Device accumulators for one `(…, N)` array + `(N,)` codes problem."""
     device = default_device()
     np_dt = np_dtype_of(array)
-    vals = to_device(array, device)
+    # A view whose reduced (last) axis is OUTERMOST in memory — e.g. a (time, lat, lon) array handed
+    # over as array.transpose(1, 2, 0), which is what moving the grouped dim to the end produces
+    # (flox/core.py:1014-1018, xarray.py:361-373) — is consumed in place as values[1, n, B]; the
+    # reference gathers / copies it instead.
+    time_major = None
+    if np.ndim(array) >= 2:
+        moved = array.movedim(-1, 0) if is_torch(array) else np.moveaxis(array, -1, 0)
+        contiguous = (lambda t: t.is_contiguous()) if is_torch(array) else (lambda t: t.flags.c_contiguous)
+        if not contiguous(array) and contiguous(moved):
+            time_major = moved
+    vals = to_device(time_major if time_major is not None else array, device)
     kdt = kernel_dtype(vals.dtype)
     if vals.dtype != kdt:
         vals = vals.to(kdt)
     codes = _codes_to_device(group_idx, device)
-    if vals.ndim == 0 or vals.shape[-1] != codes.numel():
+    n_reduced = vals.shape[0] if time_major is not None else (vals.shape[-1] if vals.ndim else -1)
+    if vals.ndim == 0 or n_reduced != codes.numel():
         raise ValueError("array.shape[-1] must equal len(group_idx)")
     if size is None:
         size = int(codes.max().item()) + 1 if codes.numel() else 0
+    if time_major is not None:
+        lead = tuple(vals.shape[1:])
+        A, B = 1, math.prod(lead)
+        acc = GroupedAccumulators([(vals.reshape(1, -1, B), codes)], 1, B, int(size), kdt, device)
+        acc.np_dtype = np_dt
+        return acc, lead, int(size)
     lead = tuple(vals.shape[:-1])
     A = math.prod(lead)
     acc = GroupedAccumulators([(vals.reshape(A, -1, 1), codes)], A, 1, int(size), kdt, device)

@@ -27,6 +27,7 @@ class ChunkedArray:
             if tuple(c.shape[:-1]) != lead:
                 raise ValueError("chunks must agree on all but the last axis")
         self.chunks = chunks
+        self._sizes = tuple(int(c.shape[-1]) for c in chunks)
 
     # -- construction ------------------------------------------------------------------------
     @classmethod
@@ -41,7 +42,7 @@ class ChunkedArray:
 
     @property
     def chunk_sizes(self) -> tuple[int, ...]:
-        return tuple(int(c.shape[-1]) for c in self.chunks)
+        return self._sizes
 
     @property
     def shape(self) -> tuple[int, ...]:
@@ -87,7 +88,16 @@ class ChunkedArray:
     def factorize_chunks(bys, expected_groups, sort: bool = True):
         """Per-chunk factorization against KNOWN expected groups (flox/factorize.py:241-268:
         the `any_by_dask` branch maps `_lazy_factorize_wrapper` over blocks)."""
-        from .factorize import _factorize_multiple
+        from .factorize import _factorize_multiple, _is_int_index, int_label_encoder
+
+        if len(bys) == 1 and is_chunked(bys[0]) and _is_int_index(expected_groups[0]):
+            first = bys[0].chunks[0]
+            if is_torch(first) and first.dtype in (torch.int32, torch.int64):
+                enc = int_label_encoder(expected_groups[0], sort)
+                if enc.mode == "passthrough":  # labels already are the codes: nothing to do per chunk
+                    return (bys[0],), (enc.groups,), (len(enc.groups),)
+                if enc.mode == "lut":
+                    return (bys[0].map(enc),), (enc.groups,), (len(enc.groups),)
 
         template = next(b for b in bys if is_chunked(b))
         per_by_chunks = []

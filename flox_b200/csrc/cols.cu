@@ -1,0 +1,266 @@
+// "Column-owner" kernels for chunks with kept trailing dims: values[A, n, B] with B > 1, labels along n.
+// This is BASELINE config 3's native layout (time, lat, lon) grouped by time.month: the reference
+// transposes the reduced axis to the end and copies (flox/core.py:1014-1018, _move_reduce_dims_to_end +
+// reshape); here the array is consumed as it lies in memory.
+//
+// A thread owns VEC adjacent columns b..b+VEC-1 (one 16-byte load per row).  Rows are visited GROUP BY
+// GROUP through a (code-sorted) row permutation built once per label vector by floxb_group_index, so
+// the running result of the current group lives in REGISTERS: no atomics, no shared memory, any G.
+// Each (a, b, g) bin is written exactly once per launch by its owner thread.
+// HBM traffic: every value read once (4 B / element for f32), labels read once to build the
+// permutation; accumulators written once.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace floxb {
+
+// ---- group index: counting sort of row numbers by code -------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_gi_count(const CT* __restrict__ codes, int64_t n, int64_t G, unsigned long long* __restrict__ goff) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const CT c = codes[i];
+    if ((unsigned long long)c < (unsigned long long)G) atomicAdd(&goff[(int64_t)c + 1], 1ull);
+  }
+}
+
+// single-block exclusive scan in place over goff[0..G] (goff[0] == 0 on entry), copy to cursor
+__global__ void __launch_bounds__(1024)
+k_gi_scan(unsigned long long* __restrict__ goff, unsigned long long* __restrict__ cursor, int64_t G) {
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 1; base <= G; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    unsigned long long v = (i <= G) ? goff[i] : 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long t = warp_tot[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, t, d);
+        if (lane >= d) t += y;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const unsigned long long incl = x + (warp ? warp_tot[warp - 1] : 0ull) + carry;
+    if (i <= G) {
+      goff[i] = incl;                 // inclusive count up to group i-1  == start of group i
+      if (i < G) cursor[i] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cursor[0] = 0ull;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_gi_scatter(const CT* __restrict__ codes, int64_t n, int64_t G, unsigned long long* __restrict__ cursor,
+             long long* __restrict__ perm) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const CT c = codes[i];
+    if ((unsigned long long)c < (unsigned long long)G) perm[atomicAdd(&cursor[(int64_t)c], 1ull)] = i;
+  }
+}
+
+// ---- column-owner reductions ------------------------------------------------------------------------
+template <typename VT, int VEC> struct ColVec { VT v[VEC]; };
+
+template <typename VT, int VEC> __device__ __forceinline__ ColVec<VT, VEC> load_cols(const VT* p) {
+  ColVec<VT, VEC> r;
+  if constexpr (VEC == 4 && sizeof(VT) == 4) {
+    const int4 q = ldg_stream(reinterpret_cast<const int4*>(p));
+    const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.v[k] = *reinterpret_cast<const VT*>(&w[k]);
+  } else if constexpr (VEC == 2 && sizeof(VT) == 8) {
+    const longlong2 q = ldg_stream(reinterpret_cast<const longlong2*>(p));
+    const long long w[2] = {q.x, q.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) r.v[k] = *reinterpret_cast<const VT*>(&w[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r.v[k] = __ldg(p + k);
+  }
+  return r;
+}
+
+// MODE: 0 sum, 1 prod, 2 sumsq, 3 max, 4 min  (accumulator: wide sum, or order-preserving key)
+template <typename VT, int MODE> struct ColAcc {
+  using AccT = typename Acc<VT>::type;
+  using T = typename std::conditional<(MODE >= 3), long long, AccT>::type;
+  static __device__ __forceinline__ T ident() {
+    if constexpr (MODE == 1) return (T)1;
+    else if constexpr (MODE == 3) return INT64_MIN;
+    else if constexpr (MODE == 4) return INT64_MAX;
+    else return (T)0;
+  }
+  static __device__ __forceinline__ T step(T a, VT v) {
+    if constexpr (MODE == 0) return a + (AccT)v;
+    else if constexpr (MODE == 1) return a * (AccT)v;
+    else if constexpr (MODE == 2) return a + (AccT)v * (AccT)v;
+    else if constexpr (MODE == 3) { const long long k = (long long)Key<VT>::enc(v); return k > a ? k : a; }
+    else { const long long k = (long long)Key<VT>::enc(v); return k < a ? k : a; }
+  }
+  static __device__ __forceinline__ T merge(T a, T b) {
+    if constexpr (MODE == 0 || MODE == 2) return a + b;
+    else if constexpr (MODE == 1) return a * b;
+    else if constexpr (MODE == 3) return a > b ? a : b;
+    else return a < b ? a : b;
+  }
+};
+
+template <typename VT, int MODE, int VEC, int UNROLL>
+__global__ void __launch_bounds__(128)
+k_cols(const VT* __restrict__ vals, const long long* __restrict__ perm, const unsigned long long* __restrict__ goff,
+       int64_t n, int64_t B, int64_t G, typename ColAcc<VT, MODE>::T* __restrict__ gacc,
+       unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan, int accumulate) {
+  using CA = ColAcc<VT, MODE>;
+  using T = typename CA::T;
+  const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (col >= B) return;
+  const int64_t a = blockIdx.y;
+  const VT* __restrict__ base = vals + a * n * B + col;
+  const int ncol = (B - col < VEC) ? (int)(B - col) : VEC;  // only when B % VEC != 0 (scalar VEC == 1 otherwise)
+  for (int64_t g = 0; g < G; ++g) {
+    T acc[VEC];
+    unsigned cnt[VEC], nan[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { acc[k] = CA::ident(); cnt[k] = 0u; nan[k] = 0u; }
+    const int64_t lo = (int64_t)goff[g], hi = (int64_t)goff[g + 1];
+    int64_t r = lo;
+    for (; r + UNROLL <= hi; r += UNROLL) {
+      ColVec<VT, VEC> x[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) x[u] = load_cols<VT, VEC>(base + perm[r + u] * B);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const VT v = x[u].v[k];
+          if (is_nan(v)) nan[k]++; else { acc[k] = CA::step(acc[k], v); cnt[k]++; }
+        }
+      }
+    }
+    for (; r < hi; ++r) {
+      const ColVec<VT, VEC> x = load_cols<VT, VEC>(base + perm[r] * B);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const VT v = x.v[k];
+        if (is_nan(v)) nan[k]++; else { acc[k] = CA::step(acc[k], v); cnt[k]++; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      if (k < ncol) {
+        const int64_t bin = (a * B + col + k) * G + g;
+        if (accumulate) {
+          gacc[bin] = CA::merge(gacc[bin], acc[k]);
+          gcnt[bin] += cnt[k];
+          gnan[bin] += nan[k];
+        } else {
+          gacc[bin] = acc[k];
+          gcnt[bin] = cnt[k];
+          gnan[bin] = nan[k];
+        }
+      }
+    }
+  }
+}
+
+template <typename VT, int MODE>
+int launch_cols(const void* values, const int64_t* perm, const int64_t* goff, int64_t A, int64_t n, int64_t B, int64_t G,
+                void* acc, int64_t* cnt, int64_t* nnan, int init, cudaStream_t st) {
+  using T = typename ColAcc<VT, MODE>::T;
+  if (A * B * G == 0) return FLOXB_OK;
+  if (A > 65535) return FLOXB_ERANGE;
+  const VT* v = reinterpret_cast<const VT*>(values);
+  auto* p = reinterpret_cast<const long long*>(perm);
+  auto* o = reinterpret_cast<const unsigned long long*>(goff);
+  T* ga = reinterpret_cast<T*>(acc);
+  auto* gc = reinterpret_cast<unsigned long long*>(cnt);
+  auto* gn = reinterpret_cast<unsigned long long*>(nnan);
+  constexpr int VEC = 16 / sizeof(VT);
+  const bool vec_ok = (B % VEC == 0) && ((reinterpret_cast<uintptr_t>(values) & 15) == 0);
+  if (vec_ok) {
+    const int64_t threads = B / VEC;
+    dim3 grid((unsigned)((threads + 127) / 128), (unsigned)A);
+    k_cols<VT, MODE, VEC, 8><<<grid, 128, 0, st>>>(v, p, o, n, B, G, ga, gc, gn, init ? 0 : 1);
+  } else {
+    dim3 grid((unsigned)((B + 127) / 128), (unsigned)A);
+    k_cols<VT, MODE, 1, 8><<<grid, 128, 0, st>>>(v, p, o, n, B, G, ga, gc, gn, init ? 0 : 1);
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+template <typename VT>
+int cols_mode(int mode, const void* values, const int64_t* perm, const int64_t* goff, int64_t A, int64_t n, int64_t B,
+              int64_t G, void* acc, int64_t* cnt, int64_t* nnan, int init, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch_cols<VT, 0>(values, perm, goff, A, n, B, G, acc, cnt, nnan, init, st);
+    case 1: return launch_cols<VT, 1>(values, perm, goff, A, n, B, G, acc, cnt, nnan, init, st);
+    case 2: return launch_cols<VT, 2>(values, perm, goff, A, n, B, G, acc, cnt, nnan, init, st);
+    case 3: return launch_cols<VT, 3>(values, perm, goff, A, n, B, G, acc, cnt, nnan, init, st);
+    case 4: return launch_cols<VT, 4>(values, perm, goff, A, n, B, G, acc, cnt, nnan, init, st);
+  }
+  return FLOXB_EINVAL;
+}
+
+}  // namespace floxb
+
+using namespace floxb;
+
+extern "C" int floxb_group_index(const void* codes, int code_dtype, int64_t n, int64_t n_groups, int64_t* perm,
+                                 int64_t* group_offsets, int64_t* cursor, void* stream) {
+  if (n < 0 || n_groups < 0) return FLOXB_EINVAL;
+  if (!group_offsets || (n_groups > 0 && !cursor) || (n > 0 && (!codes || !perm))) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto* goff = reinterpret_cast<unsigned long long*>(group_offsets);
+  auto* cur = reinterpret_cast<unsigned long long*>(cursor);
+  cudaMemsetAsync(goff, 0, (size_t)(n_groups + 1) * 8, st);
+  if (n_groups == 0) return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (code_dtype == FLOXB_I64) {
+    if (n > 0) k_gi_count<int64_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const int64_t*>(codes), n, n_groups, goff);
+    k_gi_scan<<<1, 1024, 0, st>>>(goff, cur, n_groups);
+    if (n > 0) k_gi_scatter<int64_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const int64_t*>(codes), n, n_groups, cur, reinterpret_cast<long long*>(perm));
+  } else if (code_dtype == FLOXB_I32) {
+    if (n > 0) k_gi_count<int32_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const int32_t*>(codes), n, n_groups, goff);
+    k_gi_scan<<<1, 1024, 0, st>>>(goff, cur, n_groups);
+    if (n > 0) k_gi_scatter<int32_t><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const int32_t*>(codes), n, n_groups, cur, reinterpret_cast<long long*>(perm));
+  } else {
+    return FLOXB_EDTYPE;
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+extern "C" int floxb_reduce_cols(const void* values, int value_dtype, const int64_t* perm, const int64_t* group_offsets,
+                                 int64_t A, int64_t n, int64_t B, int64_t n_groups, int mode, void* acc, int64_t* cnt,
+                                 int64_t* nnan, int init, void* stream) {
+  if (A < 0 || n < 0 || B < 0 || n_groups < 0) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && (!acc || !cnt || !nnan || !group_offsets || (n > 0 && (!values || !perm)))) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (value_dtype) {
+    case FLOXB_F32: return cols_mode<float>(mode, values, perm, group_offsets, A, n, B, n_groups, acc, cnt, nnan, init, st);
+    case FLOXB_F64: return cols_mode<double>(mode, values, perm, group_offsets, A, n, B, n_groups, acc, cnt, nnan, init, st);
+    case FLOXB_I32: return cols_mode<int32_t>(mode, values, perm, group_offsets, A, n, B, n_groups, acc, cnt, nnan, init, st);
+    case FLOXB_I64: return cols_mode<int64_t>(mode, values, perm, group_offsets, A, n, B, n_groups, acc, cnt, nnan, init, st);
+  }
+  return FLOXB_EDTYPE;
+}

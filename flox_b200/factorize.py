@@ -59,31 +59,64 @@ def _is_int_index(expect) -> bool:
             and expect.dtype.kind in "iu" and len(expect) > 0 and expect.is_unique)
 
 
+class IntLabelEncoder:
+    """Integer labels against KNOWN integer groups, without leaving the device:
+
+    * groups == 0..G-1 -> the labels ARE the codes ("passthrough"; kernels drop anything outside);
+    * otherwise        -> a lookup table over [min(groups), max(groups)] ("lut").
+    The reference does a host searchsorted + isin here (factorize.py:84-94).  Built once per
+    `groupby_reduce` call and reused for every chunk.
+    """
+
+    def __init__(self, expect: pd.Index, sort: bool):
+        ex = np.asarray(expect, dtype=np.int64)
+        order = np.argsort(ex, kind="stable")
+        already_sorted = bool(np.all(order == np.arange(len(ex))))
+        self.groups = expect[order] if (sort and not already_sorted) else expect
+        self.lo, self.hi = int(ex.min()), int(ex.max())
+        self.mode = None
+        self._table = None
+        self._lut: dict = {}
+        if self.lo == 0 and self.hi == len(ex) - 1 and (sort or already_sorted):
+            self.mode = "passthrough"
+        elif self.hi - self.lo < (1 << 26):
+            self.mode = "lut"
+            table = np.full(self.hi - self.lo + 1, -1, dtype=np.int64)
+            table[(ex[order] if sort else ex) - self.lo] = np.arange(len(ex))
+            self._table = table
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        if self.mode == "passthrough":
+            return flat if flat.dtype in (torch.int32, torch.int64) else flat.to(torch.int64)
+        lut = self._lut.get(flat.device)
+        if lut is None:
+            lut = self._lut[flat.device] = torch.as_tensor(self._table, device=flat.device)
+        rel = flat.to(torch.int64) - self.lo
+        inside = (rel >= 0) & (rel <= self.hi - self.lo)
+        return torch.where(inside, lut[rel.clamp(0, self.hi - self.lo)], rel.new_full((), -1))
+
+
+_last_encoder: tuple = (None, None, None)
+
+
+def int_label_encoder(expect: pd.Index, sort: bool) -> IntLabelEncoder:
+    global _last_encoder
+    if _last_encoder[0] is expect and _last_encoder[1] == sort:
+        return _last_encoder[2]
+    enc = IntLabelEncoder(expect, sort)
+    _last_encoder = (expect, sort, enc)
+    return enc
+
+
 def _factorize_single(by, expect, *, sort: bool, reindex: bool):
     """(groups Index, codes shaped like `by`) for one grouper (factorize.py:42-99)."""
     shape = tuple(by.shape)
     on_device = is_torch(by)
     flat = by.reshape(-1)
     if on_device and not flat.dtype.is_floating_point and flat.dtype != torch.bool and _is_int_index(expect):
-        # integer labels against known integer groups, without leaving the device:
-        #  * groups == 0..G-1  -> the labels are the codes (kernels drop anything outside the range);
-        #  * otherwise         -> a lookup table over [min(groups), max(groups)] (the reference does a
-        #                         host searchsorted + isin here, factorize.py:84-94).
-        ex = np.asarray(expect, dtype=np.int64)
-        order = np.argsort(ex, kind="stable")
-        groups = expect[order] if sort else expect
-        lo, hi = int(ex.min()), int(ex.max())
-        if lo == 0 and hi == len(ex) - 1 and (sort or bool(np.all(order == np.arange(len(ex))))):
-            codes = flat if flat.dtype in (torch.int32, torch.int64) else flat.to(torch.int64)
-            return groups, codes.reshape(shape)
-        if hi - lo < (1 << 26):
-            table = np.full(hi - lo + 1, -1, dtype=np.int64)
-            table[(ex[order] if sort else ex) - lo] = np.arange(len(ex))
-            lut = torch.as_tensor(table, device=flat.device)
-            rel = flat.to(torch.int64) - lo
-            inside = (rel >= 0) & (rel <= hi - lo)
-            codes = torch.where(inside, lut[rel.clamp(0, hi - lo)], rel.new_full((), -1))
-            return groups, codes.reshape(shape)
+        enc = int_label_encoder(expect, sort)
+        if enc.mode is not None:
+            return enc.groups, enc(flat).reshape(shape)
     if isinstance(expect, pd.RangeIndex):
         # labels ARE codes; anything above the range is "no group".  The reference copies and
         # overwrites (factorize.py:44-53); the kernels' range check makes both unnecessary.

@@ -123,6 +123,22 @@ class CudaKernels:
         self.launches += 1
         self._scan_launches(chunks, A, B, G, init, 1, vdt, force_path or self.force_path)
 
+    def group_index(self, codes, G: int, perm, goff, cursor):
+        self._require_cuda(codes, perm, goff, cursor)
+        rc = L.load().floxb_group_index(self._ptr(codes), dtype_code(codes.dtype), codes.numel(), G, self._ptr(perm),
+                                        self._ptr(goff), self._ptr(cursor), self._stream())
+        L.check(rc, "floxb_group_index")
+        self.launches += 1
+        self.kernel_launches += 1 + (2 if codes.numel() else 0)
+
+    def reduce_cols(self, values, perm, goff, A: int, n: int, B: int, G: int, mode: int, acc, cnt, nnan, init=True):
+        self._require_cuda(values, perm, goff, acc, cnt, nnan)
+        rc = L.load().floxb_reduce_cols(self._ptr(values), dtype_code(values.dtype), self._ptr(perm), self._ptr(goff), A, n, B,
+                                        G, mode, self._ptr(acc), self._ptr(cnt), self._ptr(nnan), int(init), self._stream())
+        L.check(rc, "floxb_reduce_cols")
+        self.launches += 1
+        self.kernel_launches += 1 if A * B * G else 0
+
     def sqdev(self, chunks: Chunks, A: int, B: int, G: int, means, skipna: bool, m2, init=True, value_dtype=None):
         arr, vdt, cdt = self._chunk_array(chunks, A, B)
         self._require_cuda(means, m2)

@@ -97,6 +97,22 @@ int floxb_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype,
                  int64_t A, int64_t B, int64_t n_groups, int is_max, int64_t* acc_key,
                  int64_t* cnt, int64_t* nnan, int init, int force_path, void* stream);
 
+/* Row permutation grouped by code, for the column-owner kernels: perm[group_offsets[g] .. group_offsets[g+1])
+ * lists the rows whose code is g (order within a group unspecified); rows with codes outside [0, n_groups) are
+ * left out.  cursor: i64[n_groups] scratch.  Replaces the stable argsort of _prepare_for_flox
+ * (flox/aggregate_flox.py:9-23) for this layout — an O(n) counting sort over the LABELS only. */
+int floxb_group_index(const void* codes, int code_dtype, int64_t n, int64_t n_groups, int64_t* perm,
+                      int64_t* group_offsets /* [n_groups+1] */, int64_t* cursor, void* stream);
+
+/* Column-owner reduction of ONE chunk values[A, n, B] (B > 1: kept trailing dims, e.g. (time, lat, lon) grouped
+ * along time — the layout flox reaches via _move_reduce_dims_to_end + reshape copy, flox/core.py:1014-1018).
+ * mode: 0 sum, 1 prod, 2 sum of squares (acc = f64/i64), 3 max, 4 min (acc = i64 keys); cnt/nnan as in
+ * floxb_moments.  No atomics: each (a, b, g) bin is produced in registers by one thread.
+ * init=1 overwrites the accumulators, init=0 merges into them. */
+int floxb_reduce_cols(const void* values, int value_dtype, const int64_t* perm, const int64_t* group_offsets,
+                      int64_t A, int64_t n, int64_t B, int64_t n_groups, int mode, void* acc, int64_t* cnt,
+                      int64_t* nnan, int init, void* stream);
+
 /* Second pass of var_chunk: sum over rows of (x - mean[group])^2
  * (flox/aggregations.py:375-387).  `means` is f64[A*B*G] (see floxb_group_means). */
 int floxb_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,

@@ -91,6 +91,53 @@ class EmuKernels:
             np.add.at(c, bins[good], 1)
             np.add.at(m, bins[valid & isn], 1)
 
+    def group_index(self, codes, G, perm, goff, cursor):
+        self.launches += 1
+        c = codes.numpy().astype(np.int64)
+        ok = (c >= 0) & (c < G)
+        rows = np.nonzero(ok)[0]
+        order = rows[np.argsort(c[rows], kind="stable")]
+        p = _np(perm)
+        p[: order.size] = order
+        counts = np.bincount(c[rows], minlength=G) if G else np.zeros(0, dtype=np.int64)
+        _np(goff)[...] = np.concatenate([[0], np.cumsum(counts)])
+
+    def reduce_cols(self, values, perm, goff, A, n, B, G, mode, acc, cnt, nnan, init=True):
+        self.launches += 1
+        v = values.numpy().reshape(A, n, B)
+        p, off = _np(perm), _np(goff)
+        a_, c_, m_ = _np(acc).reshape(A, B, G), _np(cnt).reshape(A, B, G), _np(nnan).reshape(A, B, G)
+        ident = {0: 0, 1: 1, 2: 0, 3: INT64_MIN, 4: INT64_MAX}[mode]
+        for g in range(G):
+            rows = p[off[g]:off[g + 1]]
+            x = v[:, rows, :]
+            isn = np.isnan(x) if x.dtype.kind == "f" else np.zeros(x.shape, bool)
+            good = ~isn
+            if mode in (0, 1, 2):
+                w = x.astype(a_.dtype)
+                if mode == 2:
+                    w = w * w
+                w = np.where(good, w, ident)
+                r = w.prod(axis=1) if mode == 1 else w.sum(axis=1)
+            else:
+                keys = _key_enc(np.ascontiguousarray(np.where(isn, 0, x).astype(x.dtype))).reshape(x.shape)
+                keys = np.where(good, keys, ident)
+                r = keys.max(axis=1, initial=ident) if mode == 3 else keys.min(axis=1, initial=ident)
+            cg, mg = good.sum(axis=1), isn.sum(axis=1)
+            if init:
+                a_[:, :, g], c_[:, :, g], m_[:, :, g] = r, cg, mg
+            else:
+                if mode in (0, 2):
+                    a_[:, :, g] += r
+                elif mode == 1:
+                    a_[:, :, g] *= r
+                elif mode == 3:
+                    a_[:, :, g] = np.maximum(a_[:, :, g], r)
+                else:
+                    a_[:, :, g] = np.minimum(a_[:, :, g], r)
+                c_[:, :, g] += cg
+                m_[:, :, g] += mg
+
     def group_means(self, value_dtype, acc, cnt, nnan, skipna, means):
         self.launches += 1
         a, c, m, out = _np(acc), _np(cnt), _np(nnan), _np(means)

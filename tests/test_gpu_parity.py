@@ -160,6 +160,29 @@ def test_multidim_layouts_vs_oracle():
             assert_same(got, want, what=f"{func}/{by.shape}/{kw}", **_tols(func, arr))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32])
+def test_time_major_layout_column_kernels(dtype):
+    """config-3 layout: a (time, lat, lon) array grouped along time, handed over as the
+    transposed VIEW (lat, lon, time) — consumed in place by the column-owner kernels."""
+    rng = np.random.default_rng(11)
+    T, ny, nx = 730, 36, 1024  # ny*nx = 36864 columns >= COLS_MIN_COLUMNS
+    base = (rng.random((T, ny, nx)) * 10 - 2).astype(dtype)
+    if np.dtype(dtype).kind == "f":
+        base[rng.random(T) < 0.05, 3, 5] = np.nan
+    months = (np.arange(T) // 31) % 12
+    months[months == 7] = 8
+    view = base.transpose(1, 2, 0)
+    xt = torch.as_tensor(base, device="cuda").permute(1, 2, 0)
+    for func in ("sum", "nanmean", "max", "nanmin", "count"):
+        want, _ = O.groupby_reduce(np.ascontiguousarray(view), months, func=func, expected_groups=np.arange(12))
+        got, _ = flox_b200.groupby_reduce(view, months, func=func, expected_groups=np.arange(12))
+        assert_same(got, want, what=f"cols/{func}/{np.dtype(dtype)}", **_tols(func, base))
+        got_t, _ = flox_b200.groupby_reduce(xt, torch.as_tensor(months, device="cuda"), func=func,
+                                            expected_groups=np.arange(12))
+        assert got_t.is_cuda
+        assert_same(got_t.cpu().numpy(), want, what=f"cols-torch/{func}/{np.dtype(dtype)}", **_tols(func, base))
+
+
 def test_torch_cuda_inputs_stay_on_device():
     rng = np.random.default_rng(5)
     x = rng.random(300_000).astype(np.float32)
