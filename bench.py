@@ -51,6 +51,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=20.0)
+    p.add_argument("--profile-host", action="store_true", help="cProfile 20 steps of the host-side path (stderr)")
     return p.parse_args()
 
 
@@ -59,8 +60,11 @@ def parse():
 # --------------------------------------------------------------------------------------------
 
 def cpu_chunks(nchunks: int, chunk: int, ngroups: int, seed: int = 12345):
+    # 8 distinct seeded chunks, cycled: generating one per host thread would cost more wall-clock
+    # than the timed region on a 128-core box and does not change what is timed
     rng = np.random.default_rng(seed)
-    return [(rng.random(chunk, dtype=np.float32), rng.integers(0, ngroups, chunk)) for _ in range(nchunks)]
+    distinct = [(rng.random(chunk, dtype=np.float32), rng.integers(0, ngroups, chunk)) for _ in range(min(nchunks, 8))]
+    return [distinct[i % len(distinct)] for i in range(nchunks)]
 
 
 def cpu_mapreduce(chunks, ngroups: int, func: str, threads: int):
@@ -228,12 +232,30 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # the clock sampler (an nvidia-smi child) is started BEFORE warm-up and given time to settle:
+    # its start-up takes driver locks that would otherwise stall launches inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    if rank == 0:
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 4.0:
+            time.sleep(0.05)
+    if args.profile_host and rank == 0:
+        import cProfile
+        import pstats
+
+        prof = cProfile.Profile()
+        prof.enable()
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("cumtime").print_stats(35)
+    barrier()
     l0 = k.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

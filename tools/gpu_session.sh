@@ -1,17 +1,30 @@
 #!/bin/bash
-# One GPU-box session: parity tests, kernel-variant microbench, bench, ncu launch list + full capture.
+# One GPU-box session: parity tests, kernel-variant microbench, bench, config sweep, ncu launch list + full capture.
+# Usage: bash tools/gpu_session.sh [steps...]   (default: all)
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
+STEPS="${*:-smoke pytest kbench bench configs ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/smi.txt 2>&1
 nproc > gpurun_out/nproc.txt; free -g >> gpurun_out/nproc.txt
-python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 600 python tools/kbench.py > gpurun_out/kbench.log 2>&1
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_moments_smem -s 1 -c 2 -f -o gpurun_out/prof_moments \
-    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+for s in $STEPS; do
+case $s in
+smoke)
+  python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log ;;
+pytest)
+  timeout 1200 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log ;;
+kbench)
+  KBENCH_VARIANTS="${KBENCH_VARIANTS:-0,2,7,9,14,15,16,17,18,19,20}" timeout 600 python tools/kbench.py > gpurun_out/kbench.log 2>&1 ;;
+bench)
+  timeout 900 python bench.py --steps 20 --warmup 3 --profile-host > gpurun_out/bench.log 2> gpurun_out/bench_hostprofile.log; echo "bench rc=$?" >> gpurun_out/bench.log ;;
+configs)
+  timeout 900 python tools/configs_bench.py > gpurun_out/configs.log 2>&1 ;;
+ncu)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_moments_smem -s 1 -c 2 -f -o gpurun_out/prof_moments \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
+esac
+done
 ls -la gpurun_out
-tail -5 gpurun_out/pytest_gpu.log gpurun_out/bench.log gpurun_out/smoke.log
+tail -4 gpurun_out/pytest_gpu.log gpurun_out/bench.log gpurun_out/smoke.log gpurun_out/configs.log 2>/dev/null

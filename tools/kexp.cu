@@ -5,7 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-enum Mode { FULL = 0, SUM_ONLY = 1, CNT_ONLY = 2, LOAD_ONLY = 3, PACKED32 = 4, F32_CAS = 5 };
+enum Mode { FULL = 0, SUM_ONLY = 1, CNT_ONLY = 2, LOAD_ONLY = 3, PACKED32 = 4, F32_CAS = 5, F32_FLUSH4 = 6, F32_FLUSH8 = 7,
+            F32_FLUSH16 = 8, HYBRID25 = 9, HYBRID50 = 10 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   float4 r;
@@ -67,6 +68,17 @@ k_exp(const float* __restrict__ vals, const long long* __restrict__ codes, int64
           atomicAdd(&sf32[b], x[k]);
           atomicAdd(&scnt[b], 1u);
         }
+        if (MODE == F32_FLUSH4 || MODE == F32_FLUSH8 || MODE == F32_FLUSH16) {
+          constexpr unsigned every = MODE == F32_FLUSH4 ? 4u : (MODE == F32_FLUSH8 ? 8u : 16u);
+          atomicAdd(&sf32[b], x[k]);
+          const unsigned seen = atomicAdd(&scnt[b], 1u);
+          if ((seen & (every - 1)) == every - 1) atomicAdd(&gacc[b], (double)atomicExch(&sf32[b], 0.0f));
+        }
+        if (MODE == HYBRID25 || MODE == HYBRID50) {
+          const bool to_l2 = MODE == HYBRID25 ? ((threadIdx.x & 3) == 0) : ((threadIdx.x & 1) == 0);
+          if (to_l2) atomicAdd(&gacc[b], (double)x[k]); else atomicAdd(&sacc[b], (double)x[k]);
+          atomicAdd(&scnt[b], 1u);
+        }
         if (MODE == PACKED32) {
           unsigned long long old = spk[b], assumed;
           do {
@@ -89,7 +101,7 @@ k_exp(const float* __restrict__ vals, const long long* __restrict__ codes, int64
       const unsigned long long p = spk[g];
       atomicAdd(&gacc[g], (double)__uint_as_float((unsigned)(p >> 32)));
       atomicAdd(&gcnt[g], (unsigned long long)(unsigned)p);
-    } else if (MODE == F32_CAS) {
+    } else if (MODE == F32_CAS || MODE == F32_FLUSH4 || MODE == F32_FLUSH8 || MODE == F32_FLUSH16) {
       atomicAdd(&gacc[g], (double)sf32[g]);
       atomicAdd(&gcnt[g], (unsigned long long)scnt[g]);
     } else {
@@ -130,6 +142,13 @@ extern "C" int kexp_run(int variant, const float* v, const long long* c, int64_t
     CASE(11, 256, 4, FULL)
     CASE(12, 1024, 4, LOAD_ONLY)
     CASE(13, 1024, 4, FULL)
+    CASE(14, 1024, 2, F32_FLUSH4)
+    CASE(15, 1024, 2, F32_FLUSH8)
+    CASE(16, 1024, 2, F32_FLUSH16)
+    CASE(17, 512, 4, F32_FLUSH8)
+    CASE(18, 1024, 2, HYBRID25)
+    CASE(19, 1024, 2, HYBRID50)
+    CASE(20, 1024, 4, F32_FLUSH8)
   }
   return -1;
 }
@@ -137,6 +156,8 @@ extern "C" int kexp_run(int variant, const float* v, const long long* c, int64_t
 extern "C" const char* kexp_name(int variant) {
   static const char* names[] = {"full t1024 i2", "full t1024 i1", "full t512 i4",  "full t512 i2",      "full t768 i2",
                                 "sum-only t1024 i2", "cnt-only t1024 i2", "load-only t1024 i2", "packed f32|u32 CAS64 t1024 i2",
-                                "f32 CAS + cnt t1024 i2", "load-only t512 i4", "full t256 i4", "load-only t1024 i4", "full t1024 i4"};
-  return (variant >= 0 && variant < 14) ? names[variant] : "?";
+                                "f32 CAS + cnt t1024 i2", "load-only t512 i4", "full t256 i4", "load-only t1024 i4", "full t1024 i4",
+                                "f32 flush4 t1024 i2", "f32 flush8 t1024 i2", "f32 flush16 t1024 i2", "f32 flush8 t512 i4",
+                                "hybrid25 f64 t1024 i2", "hybrid50 f64 t1024 i2", "f32 flush8 t1024 i4"};
+  return (variant >= 0 && variant < 21) ? names[variant] : "?";
 }
