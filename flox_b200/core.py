@@ -364,6 +364,11 @@ def _validate_expected_groups(nby: int, expected_groups):
     return expected_groups
 
 
+def _is_arange(ex: np.ndarray) -> bool:
+    n = ex.size
+    return bool(ex[0] == 0 and ex[-1] == n - 1 and (n < 3 or np.all(ex[1:] - ex[:-1] == 1)))
+
+
 def _choose_engine(by, agg: Aggregation) -> str:
     """The reference picks between CPU engines by sortedness (core.py:712-736); a scatter kernel
     does not care, so the answer here is always the GPU engine."""
@@ -421,6 +426,16 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
     isbins = _atleast_1d(isbin, nby)
     _assert_by_is_aligned(tuple(array.shape), bys)
     expected_groups = _validate_expected_groups(nby, expected_groups)
+    # 0..G-1 given as an integer array is a RangeIndex in disguise: treat it as one (no sort, no hash, no
+    # lookup table; labels pass straight through as codes) and hand the caller back an array at the end
+    arange_like: dict[int, np.dtype] = {}
+    if not any(isbins):
+        eg = list(expected_groups)
+        for i, ex in enumerate(eg):
+            if isinstance(ex, np.ndarray) and ex.ndim == 1 and ex.dtype.kind in "iu" and ex.size > 0 and _is_arange(ex):
+                arange_like[i] = ex.dtype
+                eg[i] = pd.RangeIndex(ex.size)
+        expected_groups = tuple(eg)
     for idx, (expect, chunked_) in enumerate(zip(expected_groups, by_is_chunked)):
         if chunked_ and expect is None:
             raise ValueError(f"`expected_groups` for array {idx} in `by` cannot be None since it is chunked.")
@@ -499,5 +514,8 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
         result = result.to(torch.bool) if is_torch(result) else result.astype(bool)
     if is_npdatetime and func != "count":
         result = result.astype(datetime_dtype)
-    groups = tuple(g.to_numpy() if isinstance(g, pd.Index) and not isinstance(g, pd.RangeIndex) else g for g in groups)
+    groups = tuple(
+        np.arange(len(g), dtype=arange_like[i]) if i in arange_like
+        else (g.to_numpy() if isinstance(g, pd.Index) and not isinstance(g, pd.RangeIndex) else g)
+        for i, g in enumerate(groups))
     return (result, *groups)

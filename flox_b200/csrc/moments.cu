@@ -10,19 +10,17 @@
 //           32-bit integer only), so the slot is updated with the compiler's LDS + ADD +
 //           ATOMS.CAST.SPIN loop, and the kernel is bound by L1TEX shared-memory WAVEFRONTS, not
 //           by HBM (ncu, profiles/r01_ncu_moments_f64cas_summary.json: l1tex 98% busy, 24
-//           wavefronts per 32 rows with an f64 slot).  For f32 values the slot is therefore an
-//           f32 PARTIAL sum (half the wavefronts of a 64-bit slot) that is drained into the f64
-//           global accumulator (atomicExch + RED.ADD.F64) every kFlushEvery-th row of that bin,
-//           so no f32 partial ever holds more than ~8 addends: worst-case relative error
-//           7 * 2^-24 = 4.2e-7 of sum|x| for pathological rounding, ~1e-8 in practice because the
-//           ~N/8 partials per group round independently — tighter than the reference's own f32
-//           pairwise reduceat.  f64 / integer values keep a 64-bit slot (exact in f64 / i64).
-//           Remaining bins are merged with one RED.ADD.F64 / RED.ADD.U64 per non-empty bin per
-//           CTA at the end.
+//           wavefronts per 32 rows with an f64 slot; a 32-bit slot costs half).  f32 sums
+//           therefore use the TWO-LEVEL kernel k_moments_smem_f32 below: a 32-bit f32 partial per
+//           slot in front of an f64 accumulator, both in shared memory.  f64 / integer values and
+//           products keep a single 64-bit slot (exact in f64 / i64).  Bins are merged into the
+//           global accumulators with one RED.ADD.F64 / RED.ADD.U64 per non-empty bin per CTA.
 //  * global (anything else): every element issues RED.ADD.F64 + RED.ADD.U64 straight to the
 //           L2-resident accumulators.
 // HBM traffic is the algorithmic minimum: every value and code is read exactly once
 // (ld.global.nc.L1::no_allocate, 128-bit), accumulators are written once.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace floxb {
@@ -45,13 +43,15 @@ template <typename VT, int OP> struct Slot {
   using type = typename Acc<VT>::type;
   static constexpr bool partial = false;
 };
-template <> struct Slot<float, FLOXB_OP_SUM> { using type = float; static constexpr bool partial = true; };
-template <> struct Slot<float, FLOXB_OP_SUMSQ> { using type = float; static constexpr bool partial = true; };
 
 // ------------------------------------------------------------------------------------------
 // shared-memory privatised bins
 // ------------------------------------------------------------------------------------------
-template <typename VT, typename CT, int OP, int THREADS, int ITERS>
+// RSHIFT: every group owns 2^RSHIFT slot copies, selected by the low lane bits.  With 32 copies the
+// lanes of a warp never share a slot and slot (c*32 + lane) sits in bank `lane`: no CAS retries and
+// no bank conflicts for small G (at G = 100 the un-replicated CAS loop is 2.6x slower than at
+// G = 1e4).  The launcher picks the largest replication that fits shared memory.
+template <typename VT, typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G,
                typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
@@ -61,35 +61,39 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using ST = typename Slot<VT, OP>::type;
   constexpr bool kPartial = Slot<VT, OP>::partial;
+  constexpr int R = 1 << RSHIFT;
+  const int S = G << RSHIFT;  // slots
   ST* sacc = reinterpret_cast<ST*>(smem_raw);
-  unsigned* scnt = reinterpret_cast<unsigned*>(sacc + G);
-  unsigned* snan = scnt + G;  // allocated only for float VT
+  unsigned* scnt = reinterpret_cast<unsigned*>(sacc + S);
+  unsigned* snan = scnt + S;  // allocated only for float VT
+  const int copy = threadIdx.x & (R - 1);
 
   const ST ident = (OP == FLOXB_OP_PROD) ? (ST)1 : (ST)0;
-  for (int g = threadIdx.x; g < G; g += THREADS) {
-    sacc[g] = ident;
-    scnt[g] = 0u;
-    if constexpr (is_float<VT>::value) snan[g] = 0u;
+  for (int s = threadIdx.x; s < S; s += THREADS) {
+    sacc[s] = ident;
+    scnt[s] = 0u;
+    if constexpr (is_float<VT>::value) snan[s] = 0u;
   }
   __syncthreads();
 
   auto accum = [&](VT v, CT c) {
     if ((unsigned long long)c < (unsigned long long)G) {
+      const int s = ((int)c << RSHIFT) | copy;
       if (is_nan(v)) {
-        if constexpr (is_float<VT>::value) atomicAdd(&snan[(int)c], 1u);
+        if constexpr (is_float<VT>::value) atomicAdd(&snan[s], 1u);
       } else if constexpr (kPartial) {
         const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
-        atomicAdd(&sacc[(int)c], w);
-        const unsigned seen = atomicAdd(&scnt[(int)c], 1u);
+        atomicAdd(&sacc[s], w);
+        const unsigned seen = atomicAdd(&scnt[s], 1u);
         if ((seen & (kFlushEvery - 1)) == kFlushEvery - 1) {
-          // drain this bin's f32 partial into the f64 accumulator; atomicExch hands the partial to
+          // drain this slot's f32 partial into the f64 accumulator; atomicExch hands the partial to
           // exactly one thread, concurrent adds land in the fresh zero
-          const float part = atomicExch(&sacc[(int)c], 0.0f);
+          const float part = atomicExch(&sacc[s], 0.0f);
           atomic_add(&gacc[(int)c], (AccT)part);
         }
       } else {
-        acc_apply_shared<AccT, OP>(&sacc[(int)c], lift<VT, OP>(v));
-        atomicAdd(&scnt[(int)c], 1u);
+        acc_apply_shared<AccT, OP>(&sacc[s], lift<VT, OP>(v));
+        atomicAdd(&scnt[s], 1u);
       }
     }
   };
@@ -123,16 +127,139 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
-    const unsigned c = scnt[g];
+    AccT tot = (OP == FLOXB_OP_PROD) ? (AccT)1 : (AccT)0;
+    unsigned long long c = 0ull, m = 0ull;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotate: conflict-free across the warp
+      const unsigned cs = scnt[s];
+      if (cs) {
+        if constexpr (OP == FLOXB_OP_PROD) tot *= (AccT)sacc[s]; else tot += (AccT)sacc[s];
+        c += cs;
+      }
+      if constexpr (is_float<VT>::value) m += snan[s];
+    }
     if (c) {
-      if constexpr (OP == FLOXB_OP_PROD) atomic_mul(&gacc[g], (AccT)sacc[g]);
-      else atomic_add(&gacc[g], (AccT)sacc[g]);
-      atomicAdd(&gcnt[g], (unsigned long long)c);
+      if constexpr (OP == FLOXB_OP_PROD) atomic_mul(&gacc[g], tot);
+      else atomic_add(&gacc[g], tot);
+      atomicAdd(&gcnt[g], c);
     }
-    if constexpr (is_float<VT>::value) {
-      const unsigned m = snan[g];
-      if (m) atomicAdd(&gnan[g], (unsigned long long)m);
+    if (m) atomicAdd(&gnan[g], m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// two-level shared-memory bins for f32 sums (the headline kernel)
+// ------------------------------------------------------------------------------------------
+// Level 1: f32 partial per slot, updated with the 32-bit CAS loop (LDS + FADD + ATOMS.CAST.SPIN: ~10
+//          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + native u32 count.
+// Level 2: f64 accumulator per slot.  Partials move to it
+//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain conflict-free LDS/STS, ~2
+//              wavefronts per 32 rows amortised, and
+//          (b) immediately, by the adding thread, when the partial it found was already >= 8x the
+//              addend (atomicExch + 64-bit CAS; rare for evenly spread groups, every ~8th add for a
+//              hot group), which bounds the rounding error of EVERY f32 add by 9 ulp(f32) of the
+//              addend regardless of how skewed the groups are.
+// Worst case |error| <= ~10 * 2^-24 * sum|x| per group; in practice ~1e-8 relative because the many
+// short partials round independently — tighter than the reference's f32 pairwise reduceat (1-2e-7).
+constexpr int kSweepTiles = 4;
+
+template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, double* __restrict__ gacc,
+                   unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
+  constexpr int TILE = THREADS * 4 * ITERS;
+  constexpr int R = 1 << RSHIFT;
+  const int S = G << RSHIFT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sacc = reinterpret_cast<double*>(smem_raw);     // [S]
+  float* spart = reinterpret_cast<float*>(sacc + S);      // [S]
+  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);  // [S]
+  unsigned* snan = scnt + S;                               // [G]
+  const int copy = threadIdx.x & (R - 1);
+  for (int s = threadIdx.x; s < S; s += THREADS) {
+    sacc[s] = 0.0;
+    spart[s] = 0.0f;
+    scnt[s] = 0u;
+  }
+  for (int g = threadIdx.x; g < G; g += THREADS) snan[g] = 0u;
+  __syncthreads();
+
+  auto accum = [&](float v, CT c) {
+    if ((unsigned long long)c < (unsigned long long)G) {
+      if (v != v) {
+        atomicAdd(&snan[(int)c], 1u);
+      } else {
+        const int s = ((int)c << RSHIFT) | copy;
+        const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
+        const float old = atomicAdd(&spart[s], w);
+        atomicAdd(&scnt[s], 1u);
+        if (fabsf(old) >= 8.0f * fabsf(w) && w != 0.0f) {
+          // the partial has outgrown its addends: hand it to the f64 level now.  atomicExch gives the
+          // partial to exactly one thread; concurrent adds land in the fresh zero.
+          const float part = atomicExch(&spart[s], 0.0f);
+          atomicAdd(&sacc[s], (double)part);
+        }
+      }
     }
+  };
+
+  int since_sweep = 0;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int ch = find_chunk(tab, tile);
+    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
+    const int64_t n = tab.n[ch];
+    const float* __restrict__ vals = reinterpret_cast<const float*>(tab.values[ch]) + base;
+    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
+    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
+    if (rows == TILE && aligned) {
+      Vec4<float> v[ITERS];
+      Vec4<CT> c[ITERS];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int off = (it * THREADS + threadIdx.x) * 4;
+        v[it] = load4<float>(vals + off);
+        c[it] = load4<CT>(codes + off);
+      }
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
+      }
+    } else {
+      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
+    }
+    if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile loop depends on blockIdx only
+      since_sweep = 0;
+      __syncthreads();
+      for (int s = threadIdx.x; s < S; s += THREADS) {
+        sacc[s] += (double)spart[s];
+        spart[s] = 0.0f;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    double tot = 0.0;
+    unsigned long long c = 0ull;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotated: conflict-free across the warp
+      const unsigned cs = scnt[s];
+      if (cs) {
+        tot += sacc[s] + (double)spart[s];
+        c += cs;
+      }
+    }
+    if (c) {
+      atomicAdd(&gacc[g], tot);
+      atomicAdd(&gcnt[g], c);
+    }
+    const unsigned m = snan[g];
+    if (m) atomicAdd(&gnan[g], (unsigned long long)m);
   }
 }
 
@@ -275,14 +402,27 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     k_fill_acc<AccT><<<blocks, 256, 0, st>>>(gacc, gcnt, gnan, nbins, (OP == FLOXB_OP_PROD) ? (AccT)1 : (AccT)0);
   }
   if (nbins == 0) return FLOXB_OK;
-  const size_t smem = smem_bytes_moments<VT, OP>(G);
+  constexpr bool kTwoLevel = std::is_same<VT, float>::value && OP != FLOXB_OP_PROD;
+  const size_t smem = kTwoLevel ? (size_t)G * 20 : smem_bytes_moments<VT, OP>(G);
   bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
   if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
 
   if (use_smem) {
     constexpr int TILE = kSmemThreads * 4 * kSmemIters;
-    auto kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters>;
+    using KernT = void (*)(const ChunkTable, int64_t, int, AccT*, unsigned long long*, unsigned long long*);
+    KernT kern;
+    size_t smem_used = smem;
+    if constexpr (kTwoLevel) {
+      auto bytes = [&](int r) { return (size_t)G * r * 16 + (size_t)G * 4; };
+      kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 0>;
+      if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = bytes(32); }
+      else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 3>; smem_used = bytes(8); }
+    } else {
+      kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 0>;
+      if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = smem * 32; }
+      else if (smem * 8 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 3>; smem_used = smem * 8; }
+    }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
       return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
@@ -303,7 +443,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
       // u32 per-CTA counters: keep rows per CTA below 2^32
       if (tiles / sm_count() * TILE >= (int64_t)1 << 32) return FLOXB_ERANGE;
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-      kern<<<grid, kSmemThreads, smem, st>>>(tab, tiles, (int)G, gacc, gcnt, gnan);
+      kern<<<grid, kSmemThreads, smem_used, st>>>(tab, tiles, (int)G, gacc, gcnt, gnan);
     }
   } else {
     for (int64_t k = 0; k < n_chunks; ++k) {
@@ -371,8 +511,8 @@ extern "C" int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int 
 }
 
 extern "C" int64_t floxb_smem_group_limit(int value_dtype, int family) {
-  // family 0 reports the PROD / f64 worst case (8-byte slot); f32 sums use 4-byte slots and fit more
-  const size_t per = (family == 0) ? (8 + 4 + ((value_dtype == FLOXB_F32 || value_dtype == FLOXB_F64) ? 4 : 0))
+  // family 0: f32 sums use the two-level kernel (20 B / group), everything else one 64-bit slot
+  const size_t per = (family == 0) ? (value_dtype == FLOXB_F32 ? 20 : (8 + 4 + (value_dtype == FLOXB_F64 ? 4 : 0)))
                                    : (((value_dtype == FLOXB_F32 || value_dtype == FLOXB_I32) ? 4 : 8) + 4 + 4);
   return (int64_t)(kSmemBudget / per);
 }

@@ -5,6 +5,8 @@
 //     tests/test_core.py:2287-2319).
 //   * floxb_argext : first position of the extremum per group (chunk_argreduce,
 //     flox/core.py:157-211; numpy first-occurrence semantics pinned by tests/test_core.py:388-408).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace floxb {
@@ -34,18 +36,33 @@ k_sqdev_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G,
              int skipna, double* __restrict__ gm2) {
   constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sm2 = reinterpret_cast<double*>(smem_raw);
-  double* smean = sm2 + G;
+  // f32 values: the group mean is f32-representable by construction (floxb_group_means rounds it
+  // like the reference's f32 `array_sums / array_lens`), the deviation is formed exactly in f64,
+  // and d^2 goes into an f32 PARTIAL that is drained into the f64 accumulator every 8th addend —
+  // the same shared-memory-wavefront argument as k_moments_smem (moments.cu).  Other value types
+  // keep f64 slots.
+  constexpr bool kPartial = sizeof(VT) == 4 && is_float<VT>::value;
+  using ST = typename std::conditional<kPartial, float, double>::type;
+  ST* sm2 = reinterpret_cast<ST*>(smem_raw);
+  ST* smean = sm2 + G;
+  unsigned* sseen = reinterpret_cast<unsigned*>(smean + G);  // kPartial only
   for (int g = threadIdx.x; g < G; g += THREADS) {
-    sm2[g] = 0.0;
-    smean[g] = means[g];
+    sm2[g] = (ST)0;
+    smean[g] = (ST)means[g];
+    if constexpr (kPartial) sseen[g] = 0u;
   }
   __syncthreads();
   auto accum = [&](VT v, CT c) {
     if ((unsigned long long)c < (unsigned long long)G) {
       if (is_nan(v) && skipna) return;
-      const double d = (double)v - smean[(int)c];
-      atomicAdd(&sm2[(int)c], d * d);
+      const double d = (double)v - (double)smean[(int)c];
+      if constexpr (kPartial) {
+        atomicAdd(&sm2[(int)c], (float)(d * d));
+        const unsigned seen = atomicAdd(&sseen[(int)c], 1u);
+        if ((seen & 7u) == 7u) atomicAdd(&gm2[(int)c], (double)atomicExch(&sm2[(int)c], 0.0f));
+      } else {
+        atomicAdd(&sm2[(int)c], d * d);
+      }
     }
   };
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -76,7 +93,7 @@ k_sqdev_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G,
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += THREADS) {
-    const double s = sm2[g];
+    const double s = (double)sm2[g];
     if (s != 0.0) atomicAdd(&gm2[g], s);  // NaN != 0 is true: NaN propagates
   }
 }
@@ -155,7 +172,7 @@ int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64
   const int64_t nbins = A * B * G;
   if (init && nbins > 0) k_fill_f64<<<fill_blocks(nbins), 256, 0, st>>>(m2, nbins, 0.0);
   if (nbins == 0) return FLOXB_OK;
-  const size_t smem = (size_t)G * 16;
+  const size_t smem = (size_t)G * ((sizeof(VT) == 4 && is_float<VT>::value) ? 12 : 16);
   if (A == 1 && B == 1 && smem <= 227 * 1024) {
     constexpr int TILE = kSqThreads * 4 * kSqIters;
     auto kern = k_sqdev_smem<VT, CT, kSqThreads, kSqIters>;

@@ -81,36 +81,45 @@ def _aggregate(x_chunk, combine, agg: Aggregation, expected_groups, axis, keepdi
 
 # ---- fused GPU path -------------------------------------------------------------------------------
 
-def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext):
+_CODE_DTYPES = (torch.int32, torch.int64)
+_VALUE_DTYPES = (torch.float32, torch.float64, torch.int32, torch.int64)
+
+
+def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext, need_global_index: bool = False):
     """Device tensors `(values[A, n_k, 1], codes[n_k])` for the chunks this rank owns, plus the
-    global position of each chunk's first element along the reduced axis."""
+    global position of each chunk's first element along the reduced axis (only arg-reductions need
+    positions that are global across ranks: that costs one small all-gather of shard lengths)."""
     device = default_device()
     mine = ctx.my_chunks(array.nchunks)
     sizes = array.chunk_sizes
-    if ctx.sharding == "local" and ctx.comm.enabled:
+    start = 0
+    if need_global_index and ctx.sharding == "local" and ctx.comm.enabled:
         totals = ctx.comm.all_gather_object(sum(sizes))
         start = sum(totals[: ctx.comm.rank])
-    else:
-        start = 0
-    offsets = np.concatenate([[0], np.cumsum(sizes)])[:-1] + start
+    offsets = np.concatenate([[0], np.cumsum(sizes)])[:-1]
     by_chunks = by.rechunk_like(array).chunks if is_chunked(by) else None
     lead = tuple(array.shape[:-1])
     A = math.prod(lead)
-    kdt = kernel_dtype(to_device(array.chunks[0][..., :0], device).dtype) if array.nchunks else torch.float32
+    first = array.chunks[0]
+    kdt = kernel_dtype(first.dtype if is_torch(first) else to_device(first[..., :0], device).dtype)
     chunks, index_base = [], []
     for k in mine:
-        v = to_device(array.chunks[k], device)
-        if v.dtype != kdt:
-            v = v.to(kdt)
+        v = array.chunks[k]
+        if not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
+            v = to_device(v, device)
+            if v.dtype != kdt:
+                v = v.to(kdt)
         if by_chunks is not None:
-            c = to_device(by_chunks[k], device)
+            c = by_chunks[k]
         else:
-            lo = int(offsets[k] - start)
-            c = to_device(by[..., lo:lo + sizes[k]], device)
-        if c.dtype not in (torch.int32, torch.int64):
-            c = c.to(torch.int64)
-        chunks.append((v.reshape(A, -1, 1), c.reshape(-1)))
-        index_base.append(int(offsets[k]))
+            lo = int(offsets[k])
+            c = by[..., lo:lo + sizes[k]]
+        if not (is_torch(c) and c.device == device and c.dtype in _CODE_DTYPES and c.is_contiguous()):
+            c = to_device(c, device)
+            if c.dtype not in _CODE_DTYPES:
+                c = c.to(torch.int64)
+        chunks.append((v.view(A, -1, 1), c.view(-1)))
+        index_base.append(int(offsets[k]) + start)
     return chunks, index_base, lead, A, kdt, device
 
 
@@ -122,7 +131,7 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
         raise NotImplementedError("chunked inputs are grouped by 1-D labels along the chunked (last) axis")
     ctx = parallel.current()
     G = len(expected_groups)
-    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx)
+    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg))
     acc = GroupedAccumulators(chunks, A, 1, G, kdt, device, index_base=index_base, comm=ctx.comm)
     like = array.chunks[0]
     array_np_dtype = array.dtype

@@ -24,6 +24,15 @@ ncu)
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_moments_smem -s 1 -c 2 -f -o gpurun_out/prof_moments \
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
+ncucols)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cols -s 1 -c 1 -f -o gpurun_out/prof_cols \
+      python tools/configs_bench.py c3 > gpurun_out/ncu_cols.log 2>&1 ;;
+dist)
+  NG=$(nvidia-smi -L | wc -l)
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+      tools/dist_check.py > gpurun_out/dist_check.log 2>&1; echo "dist_check rc=$?" >> gpurun_out/dist_check.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_multi.log 2>&1; echo "bench_multi rc=$?" >> gpurun_out/bench_multi.log ;;
 esac
 done
 ls -la gpurun_out
