@@ -63,9 +63,18 @@ class GroupedAccumulators:
     # ---- column-owner path (kept trailing dims, B > 1) ------------------------------------------
     COLS_MIN_COLUMNS = 32768  # enough independent columns to fill 148 SMs with 16-byte loads
 
+    ROWS_MIN_ROWS = 296        # row-batched (A >> 1, B == 1): at least two warps' worth of rows per SM
+    ROWS_MIN_GROUP_RUN = 32    # ... and groups long enough to keep a warp's lanes busy
+
     def _use_cols(self) -> bool:
-        return (self.B > 1 and self.A * self.B >= self.COLS_MIN_COLUMNS and self.A <= 65535 and self.nbins > 0
-                and any(c.numel() for _, c in self.chunks))
+        """Group-index (register-accumulating, atomic-free) kernels: column-owner for kept trailing
+        dims, warp-per-row for many rows sharing one label vector."""
+        if self.nbins == 0 or not any(c.numel() for _, c in self.chunks):
+            return False
+        if self.B > 1:
+            return self.A * self.B >= self.COLS_MIN_COLUMNS and self.A <= 65535
+        n_total = sum(c.numel() for _, c in self.chunks)
+        return self.A >= self.ROWS_MIN_ROWS and n_total >= self.ROWS_MIN_GROUP_RUN * self.G * len(self.chunks)
 
     def _group_index(self, k: int):
         """(perm, goff) of chunk k: rows grouped by code (one counting sort over the LABELS only)."""

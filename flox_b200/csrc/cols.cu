@@ -181,18 +181,81 @@ k_cols(const VT* __restrict__ vals, const long long* __restrict__ perm, const un
   }
 }
 
+// Row-batched layout values[A, n] (B == 1, A >> 1: e.g. (lat*lon, time), what flox's own reshape hands its
+// engines, flox/core.py:313-315).  One WARP per row: for each group the lanes stride over that group's rows
+// of the permutation (runs of consecutive time steps stay coalesced), accumulate in registers and finish
+// with a shuffle reduction; lane 0 writes the (row, group) bin.  No atomics, no shared memory.
+template <typename VT, int MODE>
+__global__ void __launch_bounds__(256)
+k_rows(const VT* __restrict__ vals, const long long* __restrict__ perm, const unsigned long long* __restrict__ goff,
+       int64_t A, int64_t n, int64_t G, typename ColAcc<VT, MODE>::T* __restrict__ gacc,
+       unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan, int accumulate) {
+  using CA = ColAcc<VT, MODE>;
+  using T = typename CA::T;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t a = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); a < A; a += warps) {
+    const VT* __restrict__ row = vals + a * n;
+    for (int64_t g = 0; g < G; ++g) {
+      T acc = CA::ident();
+      unsigned cnt = 0u, nan = 0u;
+      const int64_t lo = (int64_t)goff[g], hi = (int64_t)goff[g + 1];
+      int64_t k = lo + lane;
+      for (; k + 96 < hi; k += 128) {  // 4 independent loads in flight per lane
+        VT x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = __ldg(row + perm[k + 32 * u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (is_nan(x[u])) nan++; else { acc = CA::step(acc, x[u]); cnt++; }
+        }
+      }
+      for (; k < hi; k += 32) {
+        const VT x = __ldg(row + perm[k]);
+        if (is_nan(x)) nan++; else { acc = CA::step(acc, x); cnt++; }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const long long o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long*>(&acc), d);
+        acc = CA::merge(acc, *reinterpret_cast<const T*>(&o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        nan += __shfl_xor_sync(0xffffffffu, nan, d);
+      }
+      if (lane == 0) {
+        const int64_t bin = a * G + g;
+        if (accumulate) {
+          gacc[bin] = CA::merge(gacc[bin], acc);
+          gcnt[bin] += cnt;
+          gnan[bin] += nan;
+        } else {
+          gacc[bin] = acc;
+          gcnt[bin] = cnt;
+          gnan[bin] = nan;
+        }
+      }
+    }
+  }
+}
+
 template <typename VT, int MODE>
 int launch_cols(const void* values, const int64_t* perm, const int64_t* goff, int64_t A, int64_t n, int64_t B, int64_t G,
                 void* acc, int64_t* cnt, int64_t* nnan, int init, cudaStream_t st) {
   using T = typename ColAcc<VT, MODE>::T;
   if (A * B * G == 0) return FLOXB_OK;
-  if (A > 65535) return FLOXB_ERANGE;
   const VT* v = reinterpret_cast<const VT*>(values);
   auto* p = reinterpret_cast<const long long*>(perm);
   auto* o = reinterpret_cast<const unsigned long long*>(goff);
   T* ga = reinterpret_cast<T*>(acc);
   auto* gc = reinterpret_cast<unsigned long long*>(cnt);
   auto* gn = reinterpret_cast<unsigned long long*>(nnan);
+  if (B == 1) {  // row-batched layout: a warp per row
+    int64_t blocks = (A + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    k_rows<VT, MODE><<<(unsigned)blocks, 256, 0, st>>>(v, p, o, A, n, G, ga, gc, gn, init ? 0 : 1);
+    return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+  }
+  if (A > 65535) return FLOXB_ERANGE;
   constexpr int VEC = 16 / sizeof(VT);
   const bool vec_ok = (B % VEC == 0) && ((reinterpret_cast<uintptr_t>(values) & 15) == 0);
   if (vec_ok) {
