@@ -275,7 +275,9 @@ def run_gpu(args):
     value = world * rows / (ms_per_step * 1e-3)
 
     # ---- dominant kernel alone (roofline): floxb_moments over the same 100 chunks, CUDA events
-    chunks = [(v.reshape(1, -1, 1), c) for v, c in zip(arr.chunks, lab.chunks)]
+    # one launch covers a table of up to 48 chunks (csrc/common.cuh: kMaxChunksPerLaunch); time exactly one
+    chunks = [(v.reshape(1, -1, 1), c) for v, c in zip(arr.chunks, lab.chunks)][:48]
+    launch_rows = sum(c.numel() for _, c in chunks)
     acc = torch.empty(G, dtype=torch.float64, device=dev)
     cnt = torch.empty(G, dtype=torch.int64, device=dev)
     nnan = torch.empty(G, dtype=torch.int64, device=dev)
@@ -291,14 +293,14 @@ def run_gpu(args):
         b.record()
         b.synchronize()
         kt.append(a.elapsed_time(b))
-    launches_per_call = -(-len(chunks) // 48)
-    kernel_ms = float(np.mean(kt)) / launches_per_call
+    kernel_ms = float(np.mean(kt))
     peak, peak_src = hbm_peak()
-    achieved = BYTES_PER_ROW * (rows / launches_per_call) / (kernel_ms * 1e-3) / 1e9
+    achieved = BYTES_PER_ROW * launch_rows / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_moments_smem<float,long,SUM>", "peak_source": peak_src,
-                "kernel_ms_per_launch": kernel_ms, "launches_per_step": launches_per_call,
-                "algorithmic_bytes_per_launch": BYTES_PER_ROW * rows // launches_per_call}
+                "traffic": ncu_traffic(), "kernel": "k_moments_smem_f32<long,SUM,1024,2,0> (floxb_moments)",
+                "peak_source": peak_src, "kernel_ms_per_launch": kernel_ms, "rows_per_launch": launch_rows,
+                "launches_per_step": -(-len(arr.chunks) // 48), "algorithmic_bytes_per_launch": BYTES_PER_ROW * launch_rows,
+                "secondary_limit": "L1TEX shared-memory wavefronts (atomic CAS on privatised bins), see profiles/"}
 
     # ---- end to end: pinned host buffers -> public API -> host result
     e2e = None

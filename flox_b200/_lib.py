@@ -38,11 +38,11 @@ SIGNATURES = {
     "floxb_moments": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "floxb_minmax": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "floxb_group_index": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "floxb_reduce_cols": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "floxb_reduce_cols": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),
     "floxb_sqdev": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp]),
     "floxb_group_means": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "floxb_argext": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i32, C.POINTER(_i64), _vp, _i32, _vp]),
-    "floxb_finalize": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _i64, _i64, _f64, _i64, _i64, _vp, _vp]),
+    "floxb_finalize": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _i64, _i64, _f64, _i64, _i64, _vp, _i64, _vp]),
     "floxb_combine": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
     "floxb_var_combine": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "floxb_digitize": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),

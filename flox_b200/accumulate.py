@@ -35,6 +35,7 @@ class GroupedAccumulators:
         self._moments: dict[tuple, tuple] = {}
         self._fchunks = None
         self._gindex: dict[int, tuple] = {}
+        self._group_major: dict[int, int] = {}
         self._minmax: dict[bool, tuple] = {}
         self._var: dict[bool, tuple] = {}
         self._arg: dict[tuple, torch.Tensor] = {}
@@ -87,24 +88,36 @@ class GroupedAccumulators:
             self._gindex[k] = (perm, goff)
         return self._gindex[k]
 
-    def _reduce_cols(self, chunks, mode: int, acc, cnt, nnan):
+    def _reduce_cols(self, chunks, mode: int, acc, cnt, nnan, group_major: bool):
         first = True
         for k, (v, c) in enumerate(chunks):
             if c.numel() == 0:
                 continue
             perm, goff = self._group_index(k)
-            self.k.reduce_cols(v, perm, goff, self.A, c.numel(), self.B, self.G, mode, acc, cnt, nnan, init=first)
+            self.k.reduce_cols(v, perm, goff, self.A, c.numel(), self.B, self.G, mode, acc, cnt, nnan, init=first,
+                               group_major=group_major)
             first = False
 
-    def moments(self, op: int = L.OP_SUM, as_float: bool = False):
-        """(acc, cnt, nnan): acc = op over non-NaN values, cnt/nnan = # non-NaN / NaN values."""
+    def group_major_ab(self, acc) -> int:
+        """A*B if `acc` (as returned by moments/minmax) is laid out [G][A*B], else 0."""
+        return self._group_major.get(id(acc), 0)
+
+    def moments(self, op: int = L.OP_SUM, as_float: bool = False, standard_layout: bool = False):
+        """(acc, cnt, nnan): acc = op over non-NaN values, cnt = # non-NaN values, nnan > 0 iff NaNs.
+        With kept trailing dims the column-owner kernels write a GROUP-MAJOR layout (see
+        `group_major_ab`) unless `standard_layout` is requested (second-pass kernels index [A,B,G])."""
         as_float = bool(as_float) and not self.value_dtype.is_floating_point
+        gm = self._use_cols() and self.B > 1 and not standard_layout
+        if (op, as_float) in self._moments and standard_layout and self.group_major_ab(self._moments[(op, as_float)][0]):
+            del self._moments[(op, as_float)]
         if (op, as_float) not in self._moments:
             chunks, vdt = self._chunks_as(as_float)
             acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
             cnt, nnan = self._i64(), self._i64()
             if self._use_cols():
-                self._reduce_cols(chunks, op, acc, cnt, nnan)
+                self._reduce_cols(chunks, op, acc, cnt, nnan, gm)
+                if gm:
+                    self._group_major[id(acc)] = self._group_major[id(cnt)] = self.A * self.B
             else:
                 self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
             if self.comm:
@@ -117,7 +130,10 @@ class GroupedAccumulators:
         if is_max not in self._minmax:
             key, cnt, nnan = self._i64(), self._i64(), self._i64()
             if self._use_cols():
-                self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan)
+                gm = self.B > 1
+                self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan, gm)
+                if gm:
+                    self._group_major[id(key)] = self._group_major[id(cnt)] = self.A * self.B
             else:
                 self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
                               value_dtype=self.value_dtype)
@@ -140,7 +156,7 @@ class GroupedAccumulators:
         Always a float computation: integer values go through float64 (aggregations.py:352-387)."""
         if skipna not in self._var:
             chunks, vdt = self._chunks_as(True)
-            acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True)
+            acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True, standard_layout=True)
             means, m2 = self._f64(), self._f64()
             self.k.group_means(vdt, acc, cnt, nnan, skipna, means)
             # means come from the ALREADY MERGED sums, so M2 is about the global group mean and the
@@ -155,6 +171,8 @@ class GroupedAccumulators:
         key_ = (is_max, skipna)
         if key_ not in self._arg:
             key, cnt, nnan = self.minmax(is_max)
+            if self.group_major_ab(key):
+                raise NotImplementedError("arg-reductions with kept trailing dims are not supported on the column path")
             idx = self._i64()
             self.k.argext(self.chunks, self.A, self.B, self.G, key, nnan, skipna, self.index_base, idx, init=True,
                           value_dtype=self.value_dtype)
@@ -170,5 +188,7 @@ class GroupedAccumulators:
     def finalize(self, kind: int, acc, acc2, cnt, nnan, *, skipna: bool, out_dtype: torch.dtype, fill=None,
                  min_count: int = 0, mc_fill=None, ddof: int = 0, value_dtype=None) -> torch.Tensor:
         out = torch.empty(self.nbins, dtype=out_dtype, device=self.device)
-        self.k.finalize(kind, value_dtype or self.value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out)
+        gm = self.group_major_ab(acc) if acc is not None else self.group_major_ab(cnt)
+        self.k.finalize(kind, value_dtype or self.value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out,
+                        group_major_ab=gm)
         return out

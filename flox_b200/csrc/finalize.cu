@@ -22,10 +22,14 @@ template <typename VT, typename OT>
 __global__ void __launch_bounds__(256)
 k_finalize(int kind, const void* __restrict__ acc_, const void* __restrict__ acc2_, const long long* __restrict__ cnt,
            const long long* __restrict__ nnan, int64_t nbins, int skipna, OT fill, long long min_count, OT mc_fill,
-           long long ddof, OT* __restrict__ out) {
+           long long ddof, OT* __restrict__ out, int64_t gm_ab, int64_t gm_g) {
   using AccT = typename Acc<VT>::type;
   constexpr bool OF = is_float<OT>::value;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (int64_t)gridDim.x * blockDim.x) {
+  // gm_ab != 0: the accumulators are group-major [G][AB] (column-owner kernels); `out` is always [AB][G].
+  // Threads walk the ACCUMULATOR order so that the wide reads coalesce; the narrow writes merge in L2.
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nbins; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = j;                                             // accumulator index
+    const int64_t o = gm_ab ? (j % gm_ab) * gm_g + (j / gm_ab) : j;   // output index
     const long long c = cnt ? cnt[i] : 0, m = nnan ? nnan[i] : 0;
     const long long rows = c + m;
     const bool poisoned = (!skipna) && m > 0;  // a NaN reached a NaN-propagating reduction
@@ -78,7 +82,7 @@ k_finalize(int kind, const void* __restrict__ acc_, const void* __restrict__ acc
       default: r = fill;
     }
     if (min_count > 0 && c < min_count) r = mc_fill;
-    out[i] = r;
+    out[o] = r;
   }
 }
 
@@ -164,24 +168,25 @@ static inline int ew_blocks(int64_t n) {
 template <typename VT, typename OT>
 int launch_finalize(int kind, const void* acc, const void* acc2, const int64_t* cnt, const int64_t* nnan, int64_t nbins,
                     int skipna, double fill_f, int64_t fill_i, int64_t min_count, double mc_f, int64_t mc_i, int64_t ddof,
-                    void* out, cudaStream_t st) {
+                    void* out, int64_t gm_ab, cudaStream_t st) {
   const OT fill = is_float<OT>::value ? (OT)fill_f : (OT)fill_i;
   const OT mcf = is_float<OT>::value ? (OT)mc_f : (OT)mc_i;
   k_finalize<VT, OT><<<ew_blocks(nbins), 256, 0, st>>>(kind, acc, acc2, reinterpret_cast<const long long*>(cnt),
                                                       reinterpret_cast<const long long*>(nnan), nbins, skipna, fill,
-                                                      (long long)min_count, mcf, (long long)ddof, reinterpret_cast<OT*>(out));
+                                                      (long long)min_count, mcf, (long long)ddof, reinterpret_cast<OT*>(out),
+                                                      gm_ab, gm_ab ? nbins / gm_ab : 0);
   return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
 }
 
 template <typename VT>
 int finalize_out(int out_dtype, int kind, const void* acc, const void* acc2, const int64_t* cnt, const int64_t* nnan,
                  int64_t nbins, int skipna, double fill_f, int64_t fill_i, int64_t min_count, double mc_f, int64_t mc_i,
-                 int64_t ddof, void* out, cudaStream_t st) {
+                 int64_t ddof, void* out, int64_t gm_ab, cudaStream_t st) {
   switch (out_dtype) {
-    case FLOXB_F32: return launch_finalize<VT, float>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, st);
-    case FLOXB_F64: return launch_finalize<VT, double>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, st);
-    case FLOXB_I32: return launch_finalize<VT, int32_t>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, st);
-    case FLOXB_I64: return launch_finalize<VT, int64_t>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, st);
+    case FLOXB_F32: return launch_finalize<VT, float>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, gm_ab, st);
+    case FLOXB_F64: return launch_finalize<VT, double>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, gm_ab, st);
+    case FLOXB_I32: return launch_finalize<VT, int32_t>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, gm_ab, st);
+    case FLOXB_I64: return launch_finalize<VT, int64_t>(kind, acc, acc2, cnt, nnan, nbins, skipna, fill_f, fill_i, min_count, mc_f, mc_i, ddof, out, gm_ab, st);
   }
   return FLOXB_EDTYPE;
 }
@@ -210,17 +215,18 @@ using namespace floxb;
 extern "C" int floxb_finalize(int kind, int value_dtype, int out_dtype, const void* acc, const void* acc2,
                               const int64_t* cnt, const int64_t* nnan, int64_t n_bins, int skipna, double fill_f,
                               int64_t fill_i, int64_t min_count, double mc_fill_f, int64_t mc_fill_i, int64_t ddof,
-                              void* out, void* stream) {
+                              void* out, int64_t group_major_ab, void* stream) {
+  if (group_major_ab < 0 || (group_major_ab > 0 && n_bins % group_major_ab != 0)) return FLOXB_EINVAL;
   if (n_bins < 0) return FLOXB_EINVAL;
   if (n_bins == 0) return FLOXB_OK;
   if (!out || !cnt) return FLOXB_EINVAL;
   if (kind != FLOXB_FIN_NANLEN && kind != FLOXB_FIN_COUNT_ALL && !acc) return FLOXB_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (value_dtype) {
-    case FLOXB_F32: return finalize_out<float>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, st);
-    case FLOXB_F64: return finalize_out<double>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, st);
-    case FLOXB_I32: return finalize_out<int32_t>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, st);
-    case FLOXB_I64: return finalize_out<int64_t>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, st);
+    case FLOXB_F32: return finalize_out<float>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, group_major_ab, st);
+    case FLOXB_F64: return finalize_out<double>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, group_major_ab, st);
+    case FLOXB_I32: return finalize_out<int32_t>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, group_major_ab, st);
+    case FLOXB_I64: return finalize_out<int64_t>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, group_major_ab, st);
   }
   return FLOXB_EDTYPE;
 }

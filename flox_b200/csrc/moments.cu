@@ -152,17 +152,23 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // two-level shared-memory bins for f32 sums (the headline kernel)
 // ------------------------------------------------------------------------------------------
 // Level 1: f32 partial per slot, updated with the 32-bit CAS loop (LDS + FADD + ATOMS.CAST.SPIN: ~10
-//          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + native u32 count.
-// Level 2: f64 accumulator per slot.  Partials move to it
-//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain conflict-free LDS/STS, ~2
-//              wavefronts per 32 rows amortised, and
-//          (b) immediately, by the adding thread, when the partial it found was already >= 8x the
-//              addend (atomicExch + 64-bit CAS; rare for evenly spread groups, every ~8th add for a
-//              hot group), which bounds the rounding error of EVERY f32 add by 9 ulp(f32) of the
-//              addend regardless of how skewed the groups are.
-// Worst case |error| <= ~10 * 2^-24 * sum|x| per group; in practice ~1e-8 relative because the many
-// short partials round independently — tighter than the reference's f32 pairwise reduceat (1-2e-7).
-constexpr int kSweepTiles = 4;
+//          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + a native u32 counter of
+//          the adds SINCE THE LAST SWEEP (ATOMS.ADD, returning).
+// Level 2: f64 accumulator + u32 running count per slot.  Level 1 moves into level 2
+//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain, conflict-free LDS/STS
+//              (~1.5 wavefronts per 32 rows amortised); for evenly spread groups a partial then
+//              holds ~kSweepTiles * TILE / G addends (6.6 at G = 1e4);
+//          (b) immediately, by the adding thread, when the counter it got back says the slot already
+//              took kHotAdds adds since the last sweep (atomicExch of the partial + one 64-bit CAS).
+//              Hot or bursty groups (skewed or sorted labels) therefore never keep more than
+//              kHotAdds (+ racing) addends in an f32 partial either.
+// Worst case |error| <= ~kHotAdds * 2^-24 * sum|x| per group (9.5e-7); in practice ~1e-8 relative,
+// because the many short partials round independently (tests/test_gpu_parity.py::
+// test_f32_two_level_accuracy_under_skew) — tighter than the reference's f32 pairwise reduceat (1-2e-7).
+// NaN rows only set a per-group flag bit (nnan becomes "number of CTAs that saw a NaN in the group":
+// > 0 iff the group has NaNs, which is all floxb_finalize consults).
+constexpr int kSweepTiles = 8;
+constexpr unsigned kHotAdds = 16;
 
 template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -171,34 +177,39 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   constexpr int TILE = THREADS * 4 * ITERS;
   constexpr int R = 1 << RSHIFT;
   const int S = G << RSHIFT;
+  const int NW = (G + 31) >> 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sacc = reinterpret_cast<double*>(smem_raw);     // [S]
-  float* spart = reinterpret_cast<float*>(sacc + S);      // [S]
-  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);  // [S]
-  unsigned* snan = scnt + S;                               // [G]
+  double* sacc = reinterpret_cast<double*>(smem_raw);        // [S] level 2 sum
+  float* spart = reinterpret_cast<float*>(sacc + S);         // [S] level 1 partial
+  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);   // [S] adds since the last sweep
+  unsigned* stot = scnt + S;                                  // [S] adds before the last sweep
+  unsigned* snanbits = stot + S;                              // [NW] group-has-NaN flags
   const int copy = threadIdx.x & (R - 1);
   for (int s = threadIdx.x; s < S; s += THREADS) {
     sacc[s] = 0.0;
     spart[s] = 0.0f;
     scnt[s] = 0u;
+    stot[s] = 0u;
   }
-  for (int g = threadIdx.x; g < G; g += THREADS) snan[g] = 0u;
+  for (int w = threadIdx.x; w < NW; w += THREADS) snanbits[w] = 0u;
   __syncthreads();
 
   auto accum = [&](float v, CT c) {
     if ((unsigned long long)c < (unsigned long long)G) {
       if (v != v) {
-        atomicAdd(&snan[(int)c], 1u);
+        const unsigned bit = 1u << ((int)c & 31);
+        if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
       } else {
         const int s = ((int)c << RSHIFT) | copy;
         const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
-        const float old = atomicAdd(&spart[s], w);
-        atomicAdd(&scnt[s], 1u);
-        if (fabsf(old) >= 8.0f * fabsf(w) && w != 0.0f) {
-          // the partial has outgrown its addends: hand it to the f64 level now.  atomicExch gives the
-          // partial to exactly one thread; concurrent adds land in the fresh zero.
+        atomicAdd(&spart[s], w);
+        const unsigned since = atomicAdd(&scnt[s], 1u);
+        if (since >= kHotAdds - 1) {
+          // hot slot: hand partial and counter to level 2 now.  atomicExch gives each to exactly one
+          // thread; concurrent adds land in the fresh zeros.
           const float part = atomicExch(&spart[s], 0.0f);
           atomicAdd(&sacc[s], (double)part);
+          atomicAdd(&stot[s], atomicExch(&scnt[s], 0u));
         }
       }
     }
@@ -234,8 +245,13 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
       since_sweep = 0;
       __syncthreads();
       for (int s = threadIdx.x; s < S; s += THREADS) {
-        sacc[s] += (double)spart[s];
-        spart[s] = 0.0f;
+        const unsigned c = scnt[s];
+        if (c) {
+          sacc[s] += (double)spart[s];
+          spart[s] = 0.0f;
+          stot[s] += c;
+          scnt[s] = 0u;
+        }
       }
       __syncthreads();
     }
@@ -248,7 +264,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
 #pragma unroll 4
     for (int r = 0; r < R; ++r) {
       const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotated: conflict-free across the warp
-      const unsigned cs = scnt[s];
+      const unsigned cs = scnt[s] + stot[s];
       if (cs) {
         tot += sacc[s] + (double)spart[s];
         c += cs;
@@ -258,8 +274,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
       atomicAdd(&gacc[g], tot);
       atomicAdd(&gcnt[g], c);
     }
-    const unsigned m = snan[g];
-    if (m) atomicAdd(&gnan[g], (unsigned long long)m);
+    if (snanbits[g >> 5] & (1u << (g & 31))) atomicAdd(&gnan[g], 1ull);
   }
 }
 
@@ -403,7 +418,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   }
   if (nbins == 0) return FLOXB_OK;
   constexpr bool kTwoLevel = std::is_same<VT, float>::value && OP != FLOXB_OP_PROD;
-  const size_t smem = kTwoLevel ? (size_t)G * 20 : smem_bytes_moments<VT, OP>(G);
+  const size_t smem = kTwoLevel ? (size_t)G * 20 + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
   bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
   if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
@@ -414,7 +429,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     KernT kern;
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
-      auto bytes = [&](int r) { return (size_t)G * r * 16 + (size_t)G * 4; };
+      auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
       kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 0>;
       if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = bytes(32); }
       else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 3>; smem_used = bytes(8); }

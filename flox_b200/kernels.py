@@ -131,10 +131,12 @@ class CudaKernels:
         self.launches += 1
         self.kernel_launches += 1 + (2 if codes.numel() else 0)
 
-    def reduce_cols(self, values, perm, goff, A: int, n: int, B: int, G: int, mode: int, acc, cnt, nnan, init=True):
+    def reduce_cols(self, values, perm, goff, A: int, n: int, B: int, G: int, mode: int, acc, cnt, nnan, init=True,
+                    group_major=False):
         self._require_cuda(values, perm, goff, acc, cnt, nnan)
         rc = L.load().floxb_reduce_cols(self._ptr(values), dtype_code(values.dtype), self._ptr(perm), self._ptr(goff), A, n, B,
-                                        G, mode, self._ptr(acc), self._ptr(cnt), self._ptr(nnan), int(init), self._stream())
+                                        G, mode, self._ptr(acc), self._ptr(cnt), self._ptr(nnan), int(init), int(group_major),
+                                        self._stream())
         L.check(rc, "floxb_reduce_cols")
         self.launches += 1
         self.kernel_launches += 1 if A * B * G else 0
@@ -173,7 +175,7 @@ class CudaKernels:
 
     # -- epilogues -------------------------------------------------------------------------
     def finalize(self, kind: int, value_dtype, acc, acc2, cnt, nnan, skipna: bool, fill, min_count: int, mc_fill,
-                 ddof: int, out):
+                 ddof: int, out, group_major_ab: int = 0):
         self._require_cuda(acc, acc2, cnt, nnan, out)
 
         def split(v):
@@ -190,7 +192,7 @@ class CudaKernels:
         mf, mi = split(mc_fill)
         rc = L.load().floxb_finalize(kind, dtype_code(value_dtype), dtype_code(out.dtype), self._ptr(acc), self._ptr(acc2),
                                      self._ptr(cnt), self._ptr(nnan), out.numel(), int(skipna), ff, fi, int(min_count), mf,
-                                     mi, int(ddof), self._ptr(out), self._stream())
+                                     mi, int(ddof), self._ptr(out), int(group_major_ab), self._stream())
         L.check(rc, "floxb_finalize")
         self.launches += 1
         self.kernel_launches += 1

@@ -83,7 +83,9 @@ int64_t floxb_smem_group_limit(int value_dtype, int family /*0 moments, 1 minmax
  * (flox/aggregate_flox.py:9-23), which a scatter reduction does not need.
  *   chunks     HOST array of n_chunks descriptors
  *   acc        f64[A*B*G] for float values, i64[A*B*G] for integer values (non-NaN values only)
- *   cnt, nnan  i64[A*B*G]: number of non-NaN / NaN values per group
+ *   cnt, nnan  i64[A*B*G]: number of non-NaN values per group; nnan > 0 iff the group has NaN values
+ *              (an exact NaN count on the L2-atomic and column paths, the number of CTAs that saw a
+ *              NaN on the shared-memory f32 path)
  *   init       1 = reset the accumulators first (0 / 1 for PROD), 0 = accumulate on top
  *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics (testing / profiling) */
 int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
@@ -108,10 +110,12 @@ int floxb_group_index(const void* codes, int code_dtype, int64_t n, int64_t n_gr
  * along time — the layout flox reaches via _move_reduce_dims_to_end + reshape copy, flox/core.py:1014-1018).
  * mode: 0 sum, 1 prod, 2 sum of squares (acc = f64/i64), 3 max, 4 min (acc = i64 keys); cnt/nnan as in
  * floxb_moments.  No atomics: each (a, b, g) bin is produced in registers by one thread.
- * init=1 overwrites the accumulators, init=0 merges into them. */
+ * init=1 overwrites the accumulators, init=0 merges into them.
+ * group_major=1 (B > 1 only): accumulators are laid out [n_groups][A*B] instead of [A*B][n_groups] so that
+ * the owner threads write full sectors; pass the same A*B to floxb_finalize(group_major_ab). */
 int floxb_reduce_cols(const void* values, int value_dtype, const int64_t* perm, const int64_t* group_offsets,
                       int64_t A, int64_t n, int64_t B, int64_t n_groups, int mode, void* acc, int64_t* cnt,
-                      int64_t* nnan, int init, void* stream);
+                      int64_t* nnan, int init, int group_major, void* stream);
 
 /* Second pass of var_chunk: sum over rows of (x - mean[group])^2
  * (flox/aggregations.py:375-387).  `means` is f64[A*B*G] (see floxb_group_means). */
@@ -143,11 +147,13 @@ int floxb_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype,
  *   out_dtype  FLOXB_* of `out`
  *   fill_f/fill_i  value for groups with no rows (float / integer `out`)
  *   min_count  >0: groups with cnt < min_count receive mc_fill_* instead (core.py:438-459)
- *   ddof       VAR/STD only */
+ *   ddof       VAR/STD only
+ *   group_major_ab  0: accumulators are [A*B][G] like `out`; A*B: accumulators are [G][A*B]
+ *                   (written by floxb_reduce_cols(group_major=1)), `out` is still [A*B][G] */
 int floxb_finalize(int kind, int value_dtype, int out_dtype, const void* acc, const void* acc2,
                    const int64_t* cnt, const int64_t* nnan, int64_t n_bins, int skipna,
                    double fill_f, int64_t fill_i, int64_t min_count, double mc_fill_f,
-                   int64_t mc_fill_i, int64_t ddof, void* out, void* stream);
+                   int64_t mc_fill_i, int64_t ddof, void* out, int64_t group_major_ab, void* stream);
 
 /* Reduce `nblk` stacked accumulator blocks [nblk, n_bins] into out[n_bins]
  * (flox/dask.py:131-143).  dtype: FLOXB_F64 or FLOXB_I64. */

@@ -102,11 +102,14 @@ class EmuKernels:
         counts = np.bincount(c[rows], minlength=G) if G else np.zeros(0, dtype=np.int64)
         _np(goff)[...] = np.concatenate([[0], np.cumsum(counts)])
 
-    def reduce_cols(self, values, perm, goff, A, n, B, G, mode, acc, cnt, nnan, init=True):
+    def reduce_cols(self, values, perm, goff, A, n, B, G, mode, acc, cnt, nnan, init=True, group_major=False):
         self.launches += 1
         v = values.numpy().reshape(A, n, B)
         p, off = _np(perm), _np(goff)
-        a_, c_, m_ = _np(acc).reshape(A, B, G), _np(cnt).reshape(A, B, G), _np(nnan).reshape(A, B, G)
+        if group_major:  # [G][A*B] storage: expose it as [A, B, G] views
+            a_, c_, m_ = (_np(t).reshape(G, A, B).transpose(1, 2, 0) for t in (acc, cnt, nnan))
+        else:
+            a_, c_, m_ = _np(acc).reshape(A, B, G), _np(cnt).reshape(A, B, G), _np(nnan).reshape(A, B, G)
         ident = {0: 0, 1: 1, 2: 0, 3: INT64_MIN, 4: INT64_MAX}[mode]
         for g in range(G):
             rows = p[off[g]:off[g + 1]]
@@ -175,9 +178,20 @@ class EmuKernels:
             hit = valid & np.where(poisoned, isn, (~isn) & (keys == k[bins]))
             np.minimum.at(out, bins[hit], pos[hit])
 
-    def finalize(self, kind, value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out):
+    def finalize(self, kind, value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out, group_major_ab=0):
         self.launches += 1
         o = _np(out)
+        if group_major_ab:  # accumulators are [G][AB]; results go out as [AB][G]
+            gdim = o.size // group_major_ab
+
+            class _T:  # transposed read-only views with the torch-ish .numpy() the helpers expect
+                def __init__(self, t):
+                    self.a = None if t is None else np.ascontiguousarray(t.numpy().reshape(gdim, group_major_ab).T).reshape(-1)
+
+                def numpy(self):
+                    return self.a
+
+            acc, acc2, cnt, nnan = (None if t is None else _T(t) for t in (acc, acc2, cnt, nnan))
         c = _np(cnt).astype(np.int64)
         m = _np(nnan).astype(np.int64) if nnan is not None else np.zeros_like(c)
         rows = c + m

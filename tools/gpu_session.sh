@@ -17,6 +17,8 @@ kbench)
   KBENCH_VARIANTS="${KBENCH_VARIANTS:-0,2,7,9,14,15,16,17,18,19,20}" timeout 600 python tools/kbench.py > gpurun_out/kbench.log 2>&1 ;;
 bench)
   timeout 900 python bench.py --steps 20 --warmup 3 --profile-host > gpurun_out/bench.log 2> gpurun_out/bench_hostprofile.log; echo "bench rc=$?" >> gpurun_out/bench.log ;;
+kbench2)
+  timeout 600 python tools/kbench2.py > gpurun_out/kbench2.log 2>&1 ;;
 configs)
   timeout 900 python tools/configs_bench.py > gpurun_out/configs.log 2>&1 ;;
 ncu)
@@ -24,6 +26,9 @@ ncu)
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_moments_smem -s 1 -c 2 -f -o gpurun_out/prof_moments \
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
+ncuconfigs)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_configs.csv \
+      -k regex:floxb python tools/configs_bench.py c4 c5 rows > gpurun_out/ncu_configs.log 2>&1 ;;
 ncucols)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cols -s 1 -c 1 -f -o gpurun_out/prof_cols \
       python tools/configs_bench.py c3 > gpurun_out/ncu_cols.log 2>&1 ;;
