@@ -35,7 +35,8 @@ class GroupedAccumulators:
         self._moments: dict[tuple, tuple] = {}
         self._fchunks = None
         self._gindex: dict[int, tuple] = {}
-        self._group_major: dict[int, int] = {}
+        # accumulator layout: [A][G] when B == 1, group-major [G][A*B] when B > 1 (include/flox_b200.h)
+        self.gm_ab = self.A * self.B if self.B > 1 else 0
         self._minmax: dict[bool, tuple] = {}
         self._var: dict[bool, tuple] = {}
         self._arg: dict[tuple, torch.Tensor] = {}
@@ -50,6 +51,11 @@ class GroupedAccumulators:
 
     def _f64(self):
         return torch.empty(self.nbins, dtype=torch.float64, device=self.device)
+
+    def _count_pair(self):
+        """(both, cnt, nnan): the two i64 counters share one buffer so that ranks merge them with ONE collective."""
+        both = torch.empty(2 * self.nbins, dtype=torch.int64, device=self.device)
+        return both, both[: self.nbins], both[self.nbins:]
 
     # ---- kernel families -----------------------------------------------------------------
     def _chunks_as(self, as_float: bool):
@@ -98,48 +104,35 @@ class GroupedAccumulators:
                                group_major=group_major)
             first = False
 
-    def group_major_ab(self, acc) -> int:
-        """A*B if `acc` (as returned by moments/minmax) is laid out [G][A*B], else 0."""
-        return self._group_major.get(id(acc), 0)
-
-    def moments(self, op: int = L.OP_SUM, as_float: bool = False, standard_layout: bool = False):
-        """(acc, cnt, nnan): acc = op over non-NaN values, cnt = # non-NaN values, nnan > 0 iff NaNs.
-        With kept trailing dims the column-owner kernels write a GROUP-MAJOR layout (see
-        `group_major_ab`) unless `standard_layout` is requested (second-pass kernels index [A,B,G])."""
+    def moments(self, op: int = L.OP_SUM, as_float: bool = False):
+        """(acc, cnt, nnan): acc = op over non-NaN values, cnt = # non-NaN values, nnan > 0 iff NaNs."""
         as_float = bool(as_float) and not self.value_dtype.is_floating_point
-        gm = self._use_cols() and self.B > 1 and not standard_layout
-        if (op, as_float) in self._moments and standard_layout and self.group_major_ab(self._moments[(op, as_float)][0]):
-            del self._moments[(op, as_float)]
         if (op, as_float) not in self._moments:
             chunks, vdt = self._chunks_as(as_float)
             acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
-            cnt, nnan = self._i64(), self._i64()
+            both, cnt, nnan = self._count_pair()
             if self._use_cols():
-                self._reduce_cols(chunks, op, acc, cnt, nnan, gm)
-                if gm:
-                    self._group_major[id(acc)] = self._group_major[id(cnt)] = self.A * self.B
+                self._reduce_cols(chunks, op, acc, cnt, nnan, self.B > 1)
             else:
                 self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
             if self.comm:
                 (self.comm.prod_ if op == L.OP_PROD else self.comm.sum_)(acc)
-                self.comm.sum_(cnt, nnan)
+                self.comm.sum_(both)
             self._moments[(op, as_float)] = (acc, cnt, nnan)
         return self._moments[(op, as_float)]
 
     def minmax(self, is_max: bool):
         if is_max not in self._minmax:
-            key, cnt, nnan = self._i64(), self._i64(), self._i64()
+            key = self._i64()
+            both, cnt, nnan = self._count_pair()
             if self._use_cols():
-                gm = self.B > 1
-                self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan, gm)
-                if gm:
-                    self._group_major[id(key)] = self._group_major[id(cnt)] = self.A * self.B
+                self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan, self.B > 1)
             else:
                 self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
                               value_dtype=self.value_dtype)
             if self.comm:
                 (self.comm.max_ if is_max else self.comm.min_)(key)
-                self.comm.sum_(cnt, nnan)
+                self.comm.sum_(both)
             self._minmax[is_max] = (key, cnt, nnan)
         return self._minmax[is_max]
 
@@ -156,7 +149,7 @@ class GroupedAccumulators:
         Always a float computation: integer values go through float64 (aggregations.py:352-387)."""
         if skipna not in self._var:
             chunks, vdt = self._chunks_as(True)
-            acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True, standard_layout=True)
+            acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True)
             means, m2 = self._f64(), self._f64()
             self.k.group_means(vdt, acc, cnt, nnan, skipna, means)
             # means come from the ALREADY MERGED sums, so M2 is about the global group mean and the
@@ -171,8 +164,6 @@ class GroupedAccumulators:
         key_ = (is_max, skipna)
         if key_ not in self._arg:
             key, cnt, nnan = self.minmax(is_max)
-            if self.group_major_ab(key):
-                raise NotImplementedError("arg-reductions with kept trailing dims are not supported on the column path")
             idx = self._i64()
             self.k.argext(self.chunks, self.A, self.B, self.G, key, nnan, skipna, self.index_base, idx, init=True,
                           value_dtype=self.value_dtype)
@@ -188,7 +179,6 @@ class GroupedAccumulators:
     def finalize(self, kind: int, acc, acc2, cnt, nnan, *, skipna: bool, out_dtype: torch.dtype, fill=None,
                  min_count: int = 0, mc_fill=None, ddof: int = 0, value_dtype=None) -> torch.Tensor:
         out = torch.empty(self.nbins, dtype=out_dtype, device=self.device)
-        gm = self.group_major_ab(acc) if acc is not None else self.group_major_ab(cnt)
         self.k.finalize(kind, value_dtype or self.value_dtype, acc, acc2, cnt, nnan, skipna, fill, min_count, mc_fill, ddof, out,
-                        group_major_ab=gm)
+                        group_major_ab=self.gm_ab)
         return out

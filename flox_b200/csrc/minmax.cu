@@ -13,31 +13,37 @@ template <typename K, bool IS_MAX> __device__ __forceinline__ void key_update(K*
   if constexpr (IS_MAX) atomicMax(slot, k); else atomicMin(slot, k);
 }
 
-template <typename VT, typename CT, bool IS_MAX, int THREADS, int ITERS>
+// RSHIFT: 2^RSHIFT slot copies per group selected by the low lane bits (see k_moments_smem): with 32 copies the
+// lanes of a warp never collide on an address or a bank, which matters for small G.
+template <typename VT, typename CT, bool IS_MAX, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, long long* __restrict__ gkey,
               unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
   using K = typename Key<VT>::type;
   constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int R = 1 << RSHIFT;
+  const int S = G << RSHIFT;
   K* skey = reinterpret_cast<K*>(smem_raw);
-  unsigned* scnt = reinterpret_cast<unsigned*>(skey + G);
-  unsigned* snan = scnt + G;
+  unsigned* scnt = reinterpret_cast<unsigned*>(skey + S);
+  unsigned* snan = scnt + S;
+  const int copy = threadIdx.x & (R - 1);
   const K ident = IS_MAX ? Key<VT>::lowest : Key<VT>::highest;
-  for (int g = threadIdx.x; g < G; g += THREADS) {
-    skey[g] = ident;
-    scnt[g] = 0u;
-    snan[g] = 0u;
+  for (int s = threadIdx.x; s < S; s += THREADS) {
+    skey[s] = ident;
+    scnt[s] = 0u;
+    snan[s] = 0u;
   }
   __syncthreads();
 
   auto accum = [&](VT v, CT c) {
     if ((unsigned long long)c < (unsigned long long)G) {
+      const int s = ((int)c << RSHIFT) | copy;
       if (is_nan(v)) {
-        atomicAdd(&snan[(int)c], 1u);
+        atomicAdd(&snan[s], 1u);
       } else {
-        key_update<K, IS_MAX>(&skey[(int)c], Key<VT>::enc(v));
-        atomicAdd(&scnt[(int)c], 1u);
+        key_update<K, IS_MAX>(&skey[s], Key<VT>::enc(v));
+        atomicAdd(&scnt[s], 1u);
       }
     }
   };
@@ -71,13 +77,21 @@ k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
-    const unsigned c = scnt[g];
-    if (c) {
-      key_update<long long, IS_MAX>(&gkey[g], (long long)skey[g]);
-      atomicAdd(&gcnt[g], (unsigned long long)c);
+    K best = ident;
+    unsigned long long c = 0ull, m = 0ull;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));
+      const K k = skey[s];
+      best = IS_MAX ? (k > best ? k : best) : (k < best ? k : best);
+      c += scnt[s];
+      m += snan[s];
     }
-    const unsigned m = snan[g];
-    if (m) atomicAdd(&gnan[g], (unsigned long long)m);
+    if (c) {
+      key_update<long long, IS_MAX>(&gkey[g], (long long)best);
+      atomicAdd(&gcnt[g], c);
+    }
+    if (m) atomicAdd(&gnan[g], m);
   }
 }
 
@@ -96,7 +110,7 @@ k_minmax_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
-      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
       if (is_nan(v)) {
         atomicAdd(&gnan[bin], 1ull);
       } else {
@@ -139,7 +153,11 @@ int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
   if (force_path == 2) use_smem = false;
   if (use_smem) {
     constexpr int TILE = kMMThreads * 4 * kMMIters;
-    auto kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters>;
+    using KernT = void (*)(const ChunkTable, int64_t, int, long long*, unsigned long long*, unsigned long long*);
+    KernT kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 0>;
+    size_t smem_used = smem;
+    if (smem * 32 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 5>; smem_used = smem * 32; }
+    else if (smem * 8 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 3>; smem_used = smem * 8; }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMMSmemBudget) != cudaSuccess)
       return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
@@ -159,7 +177,7 @@ int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
       if (tiles == 0) continue;
       if (tiles / sm_count() * TILE >= (int64_t)1 << 32) return FLOXB_ERANGE;
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-      kern<<<grid, kMMThreads, smem, st>>>(tab, tiles, (int)G, gkey, gcnt, gnan);
+      kern<<<grid, kMMThreads, smem_used, st>>>(tab, tiles, (int)G, gkey, gcnt, gnan);
     }
   } else {
     for (int64_t k = 0; k < n_chunks; ++k) {

@@ -167,7 +167,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // test_f32_two_level_accuracy_under_skew) — tighter than the reference's f32 pairwise reduceat (1-2e-7).
 // NaN rows only set a per-group flag bit (nnan becomes "number of CTAs that saw a NaN in the group":
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
-constexpr int kSweepTiles = 8;
+constexpr int kSweepTiles = 16;  // tiles of THREADS*4*ITERS rows (4096 with ITERS = 1)
 constexpr unsigned kHotAdds = 16;
 
 template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
@@ -194,67 +194,122 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   for (int w = threadIdx.x; w < NW; w += THREADS) snanbits[w] = 0u;
   __syncthreads();
 
-  auto accum = [&](float v, CT c) {
-    if ((unsigned long long)c < (unsigned long long)G) {
-      if (v != v) {
-        const unsigned bit = 1u << ((int)c & 31);
-        if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
-      } else {
-        const int s = ((int)c << RSHIFT) | copy;
-        const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
-        atomicAdd(&spart[s], w);
-        const unsigned since = atomicAdd(&scnt[s], 1u);
-        if (since >= kHotAdds - 1) {
-          // hot slot: hand partial and counter to level 2 now.  atomicExch gives each to exactly one
-          // thread; concurrent adds land in the fresh zeros.
-          const float part = atomicExch(&spart[s], 0.0f);
-          atomicAdd(&sacc[s], (double)part);
-          atomicAdd(&stot[s], atomicExch(&scnt[s], 0u));
-        }
+  // One add: returns 1 when the slot turned out to be hot (>= kHotAdds adds since the last sweep).  The
+  // returned counter is only CONSUMED by the caller after a whole batch of rows, so the next row's CAS loop
+  // does not wait for it (the kernel is latency-bound: 32 warps per SM, one dependent LDS->FADD->CAS chain each).
+  auto add_row = [&](float v, CT c, int& slot) -> unsigned {
+    slot = -1;
+    if ((unsigned long long)c >= (unsigned long long)G) return 0u;
+    if (v != v) {
+      const unsigned bit = 1u << ((int)c & 31);
+      if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
+      return 0u;
+    }
+    const int sl = ((int)c << RSHIFT) | copy;
+    slot = sl;
+    const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
+    atomicAdd(&spart[sl], w);
+    return atomicAdd(&scnt[sl], 1u);
+  };
+  auto drain = [&](int sl) {
+    // hot slot: hand partial and counter to level 2 now.  atomicExch gives each to exactly one thread;
+    // concurrent adds land in the fresh zeros.
+    const float part = atomicExch(&spart[sl], 0.0f);
+    atomicAdd(&sacc[sl], (double)part);
+    atomicAdd(&stot[sl], atomicExch(&scnt[sl], 0u));
+  };
+  auto process4 = [&](const Vec4<float>& v, const Vec4<CT>& c) {
+    int sl[4];
+    unsigned since[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) since[k] = add_row(v.v[k], c.v[k], sl[k]);
+    bool any_hot = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) any_hot |= (sl[k] >= 0 && since[k] >= kHotAdds - 1);
+    if (any_hot) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (sl[k] >= 0 && since[k] >= kHotAdds - 1) drain(sl[k]);
+    }
+  };
+
+  // Software pipeline over tiles of THREADS*4 rows: the 128-bit loads of tile t+1 are in flight while the
+  // atomics of tile t run (ncu r01: the first use of a loaded register was the top stall).
+  struct Tile {
+    const float* vals;
+    const CT* codes;
+    int64_t rows;
+    bool full;
+  };
+  auto locate = [&](int64_t tile) -> Tile {
+    const int ch = find_chunk(tab, tile);
+    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
+    const int64_t n = tab.n[ch];
+    Tile t;
+    t.vals = reinterpret_cast<const float*>(tab.values[ch]) + base;
+    t.codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
+    t.rows = (n - base < TILE) ? (n - base) : TILE;
+    t.full = t.rows == TILE && ((reinterpret_cast<uintptr_t>(t.vals) | reinterpret_cast<uintptr_t>(t.codes)) & 15) == 0;
+    return t;
+  };
+  Vec4<float> v_cur[ITERS], v_nxt[ITERS];
+  Vec4<CT> c_cur[ITERS], c_nxt[ITERS];
+  auto fetch = [&](const Tile& t, Vec4<float>* v, Vec4<CT>* c) {
+    if (t.full) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int off = (it * THREADS + threadIdx.x) * 4;
+        v[it] = load4<float>(t.vals + off);
+        c[it] = load4<CT>(t.codes + off);
       }
     }
   };
 
   int since_sweep = 0;
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int ch = find_chunk(tab, tile);
-    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
-    const int64_t n = tab.n[ch];
-    const float* __restrict__ vals = reinterpret_cast<const float*>(tab.values[ch]) + base;
-    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
-    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
-    if (rows == TILE && aligned) {
-      Vec4<float> v[ITERS];
-      Vec4<CT> c[ITERS];
+  int64_t tile = blockIdx.x;
+  Tile cur{};
+  if (tile < total_tiles) {
+    cur = locate(tile);
+    fetch(cur, v_cur, c_cur);
+  }
+  while (tile < total_tiles) {
+    const int64_t next = tile + gridDim.x;
+    Tile nxt{};
+    if (next < total_tiles) {
+      nxt = locate(next);
+      fetch(nxt, v_nxt, c_nxt);
+    }
+    if (cur.full) {
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int off = (it * THREADS + threadIdx.x) * 4;
-        v[it] = load4<float>(vals + off);
-        c[it] = load4<CT>(codes + off);
-      }
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
-      }
+      for (int it = 0; it < ITERS; ++it) process4(v_cur[it], c_cur[it]);
     } else {
-      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
+      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) {
+        int sl;
+        const unsigned since = add_row(cur.vals[i], cur.codes[i], sl);
+        if (sl >= 0 && since >= kHotAdds - 1) drain(sl);
+      }
     }
     if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile loop depends on blockIdx only
       since_sweep = 0;
       __syncthreads();
-      for (int s = threadIdx.x; s < S; s += THREADS) {
-        const unsigned c = scnt[s];
+      for (int sl = threadIdx.x; sl < S; sl += THREADS) {
+        const unsigned c = scnt[sl];
         if (c) {
-          sacc[s] += (double)spart[s];
-          spart[s] = 0.0f;
-          stot[s] += c;
-          scnt[s] = 0u;
+          sacc[sl] += (double)spart[sl];
+          spart[sl] = 0.0f;
+          stot[sl] += c;
+          scnt[sl] = 0u;
         }
       }
       __syncthreads();
     }
+    cur = nxt;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      v_cur[it] = v_nxt[it];
+      c_cur[it] = c_nxt[it];
+    }
+    tile = next;
   }
   __syncthreads();
 
@@ -297,7 +352,9 @@ k_moments_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int6
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
-      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      // kept trailing dims: accumulators are GROUP-MAJOR [G][A*B], so the B values of one row land in one
+      // contiguous run (tools/kbench2.py: 2.6x the L2 atomic rate of the [A*B][G] layout at G = 1e5)
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;
       if (is_nan(v)) {
         atomicAdd(&gnan[bin], 1ull);
       } else {
@@ -424,15 +481,16 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   if (force_path == 2) use_smem = false;
 
   if (use_smem) {
-    constexpr int TILE = kSmemThreads * 4 * kSmemIters;
+    constexpr int kIters = kTwoLevel ? 1 : kSmemIters;  // the two-level kernel double-buffers 4096-row tiles
+    constexpr int TILE = kSmemThreads * 4 * kIters;
     using KernT = void (*)(const ChunkTable, int64_t, int, AccT*, unsigned long long*, unsigned long long*);
     KernT kern;
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
       auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
-      kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 0>;
-      if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = bytes(32); }
-      else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kSmemIters, 3>; smem_used = bytes(8); }
+      kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0>;
+      if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5>; smem_used = bytes(32); }
+      else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3>; smem_used = bytes(8); }
     } else {
       kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 0>;
       if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = smem * 32; }

@@ -113,7 +113,7 @@ k_sqdev_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
       if (is_nan(v) && skipna) continue;
-      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
       const double d = (double)v - means[bin];
       atomicAdd(&gm2[bin], d * d);
     }
@@ -136,7 +136,7 @@ k_argext_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
-      const int64_t bin = (a * B + b) * G + (int64_t)c;
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
       bool hit;
       if (!skipna && nnan[bin] > 0) hit = is_nan(v);          // NaN propagates: first NaN wins
       else hit = !is_nan(v) && (long long)Key<VT>::enc(v) == key[bin];

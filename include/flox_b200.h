@@ -14,7 +14,9 @@
  *   - return value: 0 on success, negative FLOXB_E* otherwise (floxb_strerror gives text);
  *   - a chunk is values[A, n, B] (C-contiguous) + codes[n]; codes outside [0, n_groups) are
  *     skipped (flox/factorize.py:44-53,201-210 + flox/core.py:381-383 fused away);
- *   - accumulators are [A, B, n_groups] and are WIDE: f64 for float inputs, i64 for integer
+ *   - accumulators are laid out [A][n_groups] when B == 1 and GROUP-MAJOR [n_groups][A*B] when B > 1 (kept
+ *     trailing dims: a row's B values then update one contiguous run); floxb_finalize(group_major_ab = A*B)
+ *     turns the latter into the reference's [A, B, n_groups] result order.  They are WIDE: f64 for float inputs, i64 for integer
  *     inputs, i64 counters.  Several calls may accumulate into the same buffers (init=0):
  *     that is flox's _simple_combine (flox/dask.py:90-144) fused into the chunk kernel.
  */

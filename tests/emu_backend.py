@@ -52,7 +52,11 @@ class EmuKernels:
             vals = v.numpy().reshape(A, n, B)
             codes = c.numpy().astype(np.int64)
             ok = (codes >= 0) & (codes < G)
-            bins = (np.arange(A)[:, None, None] * B + np.arange(B)[None, None, :]) * G + np.where(ok, codes, 0)[None, :, None]
+            ab = np.arange(A)[:, None, None] * B + np.arange(B)[None, None, :]
+            if B == 1:
+                bins = ab * G + np.where(ok, codes, 0)[None, :, None]
+            else:  # group-major [G][A*B] (include/flox_b200.h)
+                bins = np.where(ok, codes, 0)[None, :, None] * (A * B) + ab
             valid = np.broadcast_to(ok[None, :, None], vals.shape)
             yield vals, valid, bins
 

@@ -173,7 +173,7 @@ def test_time_major_layout_column_kernels(dtype):
     months[months == 7] = 8
     view = base.transpose(1, 2, 0)
     xt = torch.as_tensor(base, device="cuda").permute(1, 2, 0)
-    for func in ("sum", "nanmean", "max", "nanmin", "count"):
+    for func in ("sum", "nanmean", "max", "nanmin", "count", "nanvar"):
         want, _ = O.groupby_reduce(np.ascontiguousarray(view), months, func=func, expected_groups=np.arange(12))
         got, _ = flox_b200.groupby_reduce(view, months, func=func, expected_groups=np.arange(12))
         assert_same(got, want, what=f"cols/{func}/{np.dtype(dtype)}", **_tols(func, base))

@@ -28,7 +28,7 @@ ncu)
       python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1 ;;
 ncuconfigs)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_configs.csv \
-      -k regex:floxb python tools/configs_bench.py c4 c5 rows > gpurun_out/ncu_configs.log 2>&1 ;;
+      -k regex:^k_ python tools/configs_bench.py c4 c5 rows > gpurun_out/ncu_configs.log 2>&1 ;;
 ncucols)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cols -s 1 -c 1 -f -o gpurun_out/prof_cols \
       python tools/configs_bench.py c3 > gpurun_out/ncu_cols.log 2>&1 ;;
