@@ -19,6 +19,7 @@
 //           L2-resident accumulators.
 // HBM traffic is the algorithmic minimum: every value and code is read exactly once
 // (ld.global.nc.L1::no_allocate, 128-bit), accumulators are written once.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -170,7 +171,10 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 constexpr int kSweepTiles = 16;  // tiles of THREADS*4*ITERS rows (4096 with ITERS = 1)
 constexpr unsigned kHotAdds = 16;
 
-template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
+// BATCH: the four rows of a 128-bit load are added with OPTIMISTIC compare-and-swaps — four independent LDS,
+// four FADDs, four ATOMS.CAS in flight at once (instruction-level parallelism for a latency-bound kernel);
+// only a row whose CAS lost a race falls back to the retry loop.
+template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT, bool BATCH>
 __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, double* __restrict__ gacc,
                    unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
@@ -221,8 +225,41 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   auto process4 = [&](const Vec4<float>& v, const Vec4<CT>& c) {
     int sl[4];
     unsigned since[4];
+    if constexpr (BATCH) {
+      float w[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) since[k] = add_row(v.v[k], c.v[k], sl[k]);
+      for (int k = 0; k < 4; ++k) {
+        sl[k] = -1;
+        w[k] = (OP == FLOXB_OP_SUMSQ) ? v.v[k] * v.v[k] : v.v[k];
+        if ((unsigned long long)c.v[k] < (unsigned long long)G) {
+          if (v.v[k] != v.v[k]) {
+            const unsigned bit = 1u << ((int)c.v[k] & 31);
+            if (!(snanbits[(int)c.v[k] >> 5] & bit)) atomicOr(&snanbits[(int)c.v[k] >> 5], bit);
+          } else {
+            sl[k] = ((int)c.v[k] << RSHIFT) | copy;
+          }
+        }
+      }
+      unsigned old[4], nw[4], got[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) old[k] = sl[k] >= 0 ? __float_as_uint(spart[sl[k]]) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) nw[k] = __float_as_uint(__uint_as_float(old[k]) + w[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        got[k] = sl[k] >= 0 ? atomicCAS(reinterpret_cast<unsigned*>(&spart[sl[k]]), old[k], nw[k]) : old[k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        since[k] = 0u;
+        if (sl[k] >= 0) {
+          if (got[k] != old[k]) atomicAdd(&spart[sl[k]], w[k]);
+          since[k] = atomicAdd(&scnt[sl[k]], 1u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) since[k] = add_row(v.v[k], c.v[k], sl[k]);
+    }
     bool any_hot = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) any_hot |= (sl[k] >= 0 && since[k] >= kHotAdds - 1);
@@ -487,10 +524,11 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     KernT kern;
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
+      static const bool batch = [] { const char* e = getenv("FLOXB_F32_BATCH"); return e ? e[0] != '0' : true; }();
       auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
-      kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0>;
-      if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5>; smem_used = bytes(32); }
-      else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3>; smem_used = bytes(8); }
+      kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, false>;
+      if (bytes(32) <= kSmemBudget) { kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, false>; smem_used = bytes(32); }
+      else if (bytes(8) <= kSmemBudget) { kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, false>; smem_used = bytes(8); }
     } else {
       kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 0>;
       if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = smem * 32; }

@@ -32,7 +32,7 @@ def main():
     gen = torch.Generator(device="cuda").manual_seed(1)
     x = torch.rand(n, device="cuda", generator=gen)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    VARIANTS = [int(v) for v in os.environ.get("KBENCH_VARIANTS", ",".join(map(str, range(21)))).split(",")]
+    VARIANTS = [int(v) for v in os.environ.get("KBENCH_VARIANTS", ",".join(map(str, range(26)))).split(",")]
     for G in (10_000, 100, 1000):
         by = torch.randint(0, G, (n,), device="cuda", generator=gen, dtype=torch.int64)
         acc = torch.zeros(G, dtype=torch.float64, device="cuda")
@@ -53,8 +53,8 @@ def main():
                 ok = None
                 name = lib.kexp_name(variant).decode()
                 if name.startswith(("full", "packed", "f32", "hybrid")):
-                    ok = bool(int(cnt.sum()) == (n // (int(name.split(" t")[1].split()[0]) * 4 * int(name.split(" i")[1]))) *
-                              (int(name.split(" t")[1].split()[0]) * 4 * int(name.split(" i")[1])))
+                    t_, i_ = int(name.split(" t")[-1].split()[0]), int(name.split(" i")[-1])
+                    ok = bool(int(cnt.sum()) == (n // (t_ * 4 * i_)) * (t_ * 4 * i_))
                 row = dict(G=G, variant=variant, name=name, grid=grid, ms=ms, rows_per_s=n / ms * 1e3, gbs=12 * n / ms / 1e6, ok=ok)
                 out.append(row)
                 print(json.dumps(row), flush=True)

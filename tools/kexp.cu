@@ -6,7 +6,92 @@
 #include <stdint.h>
 
 enum Mode { FULL = 0, SUM_ONLY = 1, CNT_ONLY = 2, LOAD_ONLY = 3, PACKED32 = 4, F32_CAS = 5, F32_FLUSH4 = 6, F32_FLUSH8 = 7,
-            F32_FLUSH16 = 8, HYBRID25 = 9, HYBRID50 = 10 };
+            F32_FLUSH16 = 8, HYBRID25 = 9, HYBRID50 = 10, F32_BATCH = 11, F32_CAS_RET = 12, F32_CAS_SWEEP = 13 };
+
+__device__ __forceinline__ float4 ldg4(const float* p);
+__device__ __forceinline__ longlong2 ldg2(const long long* p);
+
+// 4 rows at a time with an OPTIMISTIC compare-and-swap each: the four LDS, the four FADDs and the four
+// ATOMS.CAS are independent instructions (ILP), only losers fall back to the retry loop.
+__device__ __forceinline__ void batch_add4(float* sf32, unsigned* scnt, const int* b, const float* x, const bool* ok) {
+  unsigned old[4], nw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) old[k] = ok[k] ? __float_as_uint(sf32[b[k]]) : 0u;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) nw[k] = __float_as_uint(__uint_as_float(old[k]) + x[k]);
+  unsigned got[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) got[k] = ok[k] ? atomicCAS(reinterpret_cast<unsigned*>(&sf32[b[k]]), old[k], nw[k]) : old[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (ok[k]) {
+      if (got[k] != old[k]) atomicAdd(&sf32[b[k]], x[k]);
+      atomicAdd(&scnt[b[k]], 1u);
+    }
+  }
+}
+
+// Same work as F32_CAS (f32 CAS loop + native count) but with the loads of the NEXT tile in flight while
+// the atomics of the current tile run (register double buffering, tile = THREADS*4 rows).
+template <int THREADS, bool BATCH>
+__global__ void __launch_bounds__(THREADS, 1)
+k_exp_pipe(const float* __restrict__ vals, const long long* __restrict__ codes, int64_t n, int G, double* __restrict__ gacc,
+           unsigned long long* __restrict__ gcnt) {
+  constexpr int TILE = THREADS * 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sf32 = reinterpret_cast<float*>(smem_raw);
+  unsigned* scnt = reinterpret_cast<unsigned*>(smem_raw + (size_t)G * 8);
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    sf32[g] = 0.f;
+    scnt[g] = 0u;
+  }
+  __syncthreads();
+  const int64_t tiles = n / TILE;
+  int64_t tile = blockIdx.x;
+  float4 v0, v1;
+  longlong2 a0, b0, a1, b1;
+  if (tile < tiles) {
+    const int off = threadIdx.x * 4;
+    v0 = ldg4(vals + tile * TILE + off);
+    a0 = ldg2(codes + tile * TILE + off);
+    b0 = ldg2(codes + tile * TILE + off + 2);
+  }
+  while (tile < tiles) {
+    const int64_t next = tile + gridDim.x;
+    if (next < tiles) {
+      const int off = threadIdx.x * 4;
+      v1 = ldg4(vals + next * TILE + off);
+      a1 = ldg2(codes + next * TILE + off);
+      b1 = ldg2(codes + next * TILE + off + 2);
+    }
+    const float x[4] = {v0.x, v0.y, v0.z, v0.w};
+    const long long cc[4] = {a0.x, a0.y, b0.x, b0.y};
+    if (BATCH) {
+      int b[4];
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ok[k] = (unsigned long long)cc[k] < (unsigned long long)G;
+        b[k] = ok[k] ? (int)cc[k] : 0;
+      }
+      batch_add4(sf32, scnt, b, x, ok);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((unsigned long long)cc[k] >= (unsigned long long)G) continue;
+        atomicAdd(&sf32[(int)cc[k]], x[k]);
+        atomicAdd(&scnt[(int)cc[k]], 1u);
+      }
+    }
+    v0 = v1; a0 = a1; b0 = b1;
+    tile = next;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    atomicAdd(&gacc[g], (double)sf32[g]);
+    atomicAdd(&gcnt[g], (unsigned long long)scnt[g]);
+  }
+}
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
   float4 r;
@@ -68,6 +153,24 @@ k_exp(const float* __restrict__ vals, const long long* __restrict__ codes, int64
           atomicAdd(&sf32[b], x[k]);
           atomicAdd(&scnt[b], 1u);
         }
+        if (MODE == F32_CAS_RET) {
+          atomicAdd(&sf32[b], x[k]);
+          csink += atomicAdd(&scnt[b], 1u);   // RETURNING counter add (ATOMS.ADD instead of ATOMS.POPC.INC)
+        }
+        if (MODE == F32_CAS_SWEEP) {
+          atomicAdd(&sf32[b], x[k]);
+          atomicAdd(&scnt[b], 1u);
+        }
+        if (MODE == F32_BATCH && k == 0) {
+          int bb[4];
+          bool ok[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ok[q] = (unsigned long long)cc[q] < (unsigned long long)G;
+            bb[q] = ok[q] ? (int)cc[q] : 0;
+          }
+          batch_add4(sf32, scnt, bb, x, ok);
+        }
         if (MODE == F32_FLUSH4 || MODE == F32_FLUSH8 || MODE == F32_FLUSH16) {
           constexpr unsigned every = MODE == F32_FLUSH4 ? 4u : (MODE == F32_FLUSH8 ? 8u : 16u);
           atomicAdd(&sf32[b], x[k]);
@@ -90,8 +193,19 @@ k_exp(const float* __restrict__ vals, const long long* __restrict__ codes, int64
         }
       }
     }
+    if (MODE == F32_CAS_SWEEP && (((tile - blockIdx.x) / gridDim.x) & 7) == 7) {
+      // barrier-fenced sweep of the f32 partials into an f64 level (kept after the counters), every 8 tiles
+      double* lvl2 = reinterpret_cast<double*>(smem_raw + (size_t)G * 12);
+      __syncthreads();
+      for (int g = threadIdx.x; g < G; g += THREADS) {
+        lvl2[g] += (double)sf32[g];
+        sf32[g] = 0.f;
+      }
+      __syncthreads();
+    }
   }
   __syncthreads();
+  if (MODE == F32_CAS_RET && csink == 42) gcnt[0] = 1;
   if (MODE == LOAD_ONLY) {
     if (sink == 123.456f && csink == 42) gacc[0] = sink;  // keep the loads alive
     return;
@@ -101,7 +215,7 @@ k_exp(const float* __restrict__ vals, const long long* __restrict__ codes, int64
       const unsigned long long p = spk[g];
       atomicAdd(&gacc[g], (double)__uint_as_float((unsigned)(p >> 32)));
       atomicAdd(&gcnt[g], (unsigned long long)(unsigned)p);
-    } else if (MODE == F32_CAS || MODE == F32_FLUSH4 || MODE == F32_FLUSH8 || MODE == F32_FLUSH16) {
+    } else if (MODE == F32_CAS || MODE == F32_CAS_RET || MODE == F32_CAS_SWEEP || MODE == F32_BATCH || MODE == F32_FLUSH4 || MODE == F32_FLUSH8 || MODE == F32_FLUSH16) {
       atomicAdd(&gacc[g], (double)sf32[g]);
       atomicAdd(&gcnt[g], (unsigned long long)scnt[g]);
     } else {
@@ -116,7 +230,7 @@ static int launch(const float* v, const long long* c, int64_t n, int G, double* 
                   cudaStream_t st) {
   auto k = k_exp<THREADS, ITERS, MODE>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  const size_t smem = (size_t)G * 12 + 16;
+  const size_t smem = (size_t)G * 20 + 16;
   k<<<grid, THREADS, smem, st>>>(v, c, n, G, acc, cnt);
   return (int)cudaGetLastError();
 }
@@ -149,6 +263,21 @@ extern "C" int kexp_run(int variant, const float* v, const long long* c, int64_t
     CASE(18, 1024, 2, HYBRID25)
     CASE(19, 1024, 2, HYBRID50)
     CASE(20, 1024, 4, F32_FLUSH8)
+    CASE(21, 1024, 2, F32_BATCH)
+    CASE(24, 1024, 2, F32_CAS_RET)
+    CASE(25, 1024, 2, F32_CAS_SWEEP)
+    case 22: {
+      auto k = k_exp_pipe<1024, false>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      k<<<grid, 1024, (size_t)G * 12 + 16, st>>>(v, c, n, G, acc, cnt);
+      return (int)cudaGetLastError();
+    }
+    case 23: {
+      auto k = k_exp_pipe<1024, true>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      k<<<grid, 1024, (size_t)G * 12 + 16, st>>>(v, c, n, G, acc, cnt);
+      return (int)cudaGetLastError();
+    }
   }
   return -1;
 }
@@ -158,6 +287,8 @@ extern "C" const char* kexp_name(int variant) {
                                 "sum-only t1024 i2", "cnt-only t1024 i2", "load-only t1024 i2", "packed f32|u32 CAS64 t1024 i2",
                                 "f32 CAS + cnt t1024 i2", "load-only t512 i4", "full t256 i4", "load-only t1024 i4", "full t1024 i4",
                                 "f32 flush4 t1024 i2", "f32 flush8 t1024 i2", "f32 flush16 t1024 i2", "f32 flush8 t512 i4",
-                                "hybrid25 f64 t1024 i2", "hybrid50 f64 t1024 i2", "f32 flush8 t1024 i4"};
-  return (variant >= 0 && variant < 21) ? names[variant] : "?";
+                                "hybrid25 f64 t1024 i2", "hybrid50 f64 t1024 i2", "f32 flush8 t1024 i4",
+                                "f32 batch4 optimistic CAS t1024 i2", "f32 CAS + cnt pipelined t1024 i1", "f32 batch4 pipelined t1024 i1",
+                                "f32 CAS + RETURNING cnt t1024 i2", "f32 CAS + cnt + sweeps t1024 i2"};
+  return (variant >= 0 && variant < 26) ? names[variant] : "?";
 }
