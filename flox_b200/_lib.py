@@ -61,6 +61,13 @@ def load():
     with _lock:
         if _lib is None:
             if not os.path.exists(LIB_PATH):
+                try:  # in-tree build with nvcc if the artefact did not travel with the checkout
+                    from . import build as _build
+
+                    _build.build()
+                except Exception:
+                    pass
+            if not os.path.exists(LIB_PATH):
                 raise FloxB200Error(
                     f"{LIB_PATH} not found: the CUDA extension has not been built "
                     "(run `python -m flox_b200.build`). flox_b200 has no CPU fallback."

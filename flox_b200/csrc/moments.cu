@@ -153,28 +153,25 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // two-level shared-memory bins for f32 sums (the headline kernel)
 // ------------------------------------------------------------------------------------------
 // Level 1: f32 partial per slot, updated with the 32-bit CAS loop (LDS + FADD + ATOMS.CAST.SPIN: ~10
-//          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + a native u32 counter of
-//          the adds SINCE THE LAST SWEEP (ATOMS.ADD, returning).
-// Level 2: f64 accumulator + u32 running count per slot.  Level 1 moves into level 2
-//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain, conflict-free LDS/STS
-//              (~1.5 wavefronts per 32 rows amortised); for evenly spread groups a partial then
-//              holds ~kSweepTiles * TILE / G addends (6.6 at G = 1e4);
-//          (b) immediately, by the adding thread, when the counter it got back says the slot already
-//              took kHotAdds adds since the last sweep (atomicExch of the partial + one 64-bit CAS).
-//              Hot or bursty groups (skewed or sorted labels) therefore never keep more than
-//              kHotAdds (+ racing) addends in an f32 partial either.
-// Worst case |error| <= ~kHotAdds * 2^-24 * sum|x| per group (9.5e-7); in practice ~1e-8 relative,
-// because the many short partials round independently (tests/test_gpu_parity.py::
-// test_f32_two_level_accuracy_under_skew) — tighter than the reference's f32 pairwise reduceat (1-2e-7).
+//          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + a native u32 counter
+//          (ATOMS.ADD; the returned old count costs nothing extra — tools/kbench.py v24 vs v9).
+// Level 2: f64 accumulator per slot.  Level 1 moves into level 2
+//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain, conflict-free LDS/STS; for
+//              evenly spread groups a partial then holds ~kSweepTiles * TILE / G addends (6.6 at G = 1e4);
+//          (b) immediately, by the thread whose counter value shows that the slot just completed another
+//              kDrainEvery adds (atomicExch of the partial + one 64-bit CAS), so hot or bursty groups
+//              (skewed or sorted labels) never keep more than kDrainEvery (+ racing) addends in f32.
+// Worst case |error| <= kDrainEvery * 2^-24 * sum|x| per group; measured ~1e-9..1e-8 relative, because the
+// many short partials round independently (tests/test_gpu_parity.py::test_f32_two_level_accuracy_under_skew)
+// — tighter than the reference's own f32 pairwise reduceat (1-2e-7).
 // NaN rows only set a per-group flag bit (nnan becomes "number of CTAs that saw a NaN in the group":
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
+// The tile loop is software-pipelined (loads of tile t+1 in flight during the atomics of tile t) and walks
+// the chunk table monotonically (no per-tile binary search): tools/kbench.py v22 vs v9.
 constexpr int kSweepTiles = 16;  // tiles of THREADS*4*ITERS rows (4096 with ITERS = 1)
-constexpr unsigned kHotAdds = 16;
+constexpr unsigned kDrainEvery = 32;  // power of two
 
-// BATCH: the four rows of a 128-bit load are added with OPTIMISTIC compare-and-swaps — four independent LDS,
-// four FADDs, four ATOMS.CAS in flight at once (instruction-level parallelism for a latency-bound kernel);
-// only a row whose CAS lost a race falls back to the retry loop.
-template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT, bool BATCH>
+template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, double* __restrict__ gacc,
                    unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
@@ -185,101 +182,44 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sacc = reinterpret_cast<double*>(smem_raw);        // [S] level 2 sum
   float* spart = reinterpret_cast<float*>(sacc + S);         // [S] level 1 partial
-  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);   // [S] adds since the last sweep
-  unsigned* stot = scnt + S;                                  // [S] adds before the last sweep
-  unsigned* snanbits = stot + S;                              // [NW] group-has-NaN flags
+  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);   // [S] number of adds
+  unsigned* snanbits = scnt + S;                              // [NW] group-has-NaN flags
   const int copy = threadIdx.x & (R - 1);
   for (int s = threadIdx.x; s < S; s += THREADS) {
     sacc[s] = 0.0;
     spart[s] = 0.0f;
     scnt[s] = 0u;
-    stot[s] = 0u;
   }
   for (int w = threadIdx.x; w < NW; w += THREADS) snanbits[w] = 0u;
   __syncthreads();
 
-  // One add: returns 1 when the slot turned out to be hot (>= kHotAdds adds since the last sweep).  The
-  // returned counter is only CONSUMED by the caller after a whole batch of rows, so the next row's CAS loop
-  // does not wait for it (the kernel is latency-bound: 32 warps per SM, one dependent LDS->FADD->CAS chain each).
-  auto add_row = [&](float v, CT c, int& slot) -> unsigned {
-    slot = -1;
-    if ((unsigned long long)c >= (unsigned long long)G) return 0u;
+  auto add_row = [&](float v, CT c) {
+    if ((unsigned long long)c >= (unsigned long long)G) return;
     if (v != v) {
       const unsigned bit = 1u << ((int)c & 31);
       if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
-      return 0u;
+      return;
     }
     const int sl = ((int)c << RSHIFT) | copy;
-    slot = sl;
     const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
     atomicAdd(&spart[sl], w);
-    return atomicAdd(&scnt[sl], 1u);
-  };
-  auto drain = [&](int sl) {
-    // hot slot: hand partial and counter to level 2 now.  atomicExch gives each to exactly one thread;
-    // concurrent adds land in the fresh zeros.
-    const float part = atomicExch(&spart[sl], 0.0f);
-    atomicAdd(&sacc[sl], (double)part);
-    atomicAdd(&stot[sl], atomicExch(&scnt[sl], 0u));
-  };
-  auto process4 = [&](const Vec4<float>& v, const Vec4<CT>& c) {
-    int sl[4];
-    unsigned since[4];
-    if constexpr (BATCH) {
-      float w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        sl[k] = -1;
-        w[k] = (OP == FLOXB_OP_SUMSQ) ? v.v[k] * v.v[k] : v.v[k];
-        if ((unsigned long long)c.v[k] < (unsigned long long)G) {
-          if (v.v[k] != v.v[k]) {
-            const unsigned bit = 1u << ((int)c.v[k] & 31);
-            if (!(snanbits[(int)c.v[k] >> 5] & bit)) atomicOr(&snanbits[(int)c.v[k] >> 5], bit);
-          } else {
-            sl[k] = ((int)c.v[k] << RSHIFT) | copy;
-          }
-        }
-      }
-      unsigned old[4], nw[4], got[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) old[k] = sl[k] >= 0 ? __float_as_uint(spart[sl[k]]) : 0u;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) nw[k] = __float_as_uint(__uint_as_float(old[k]) + w[k]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        got[k] = sl[k] >= 0 ? atomicCAS(reinterpret_cast<unsigned*>(&spart[sl[k]]), old[k], nw[k]) : old[k];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        since[k] = 0u;
-        if (sl[k] >= 0) {
-          if (got[k] != old[k]) atomicAdd(&spart[sl[k]], w[k]);
-          since[k] = atomicAdd(&scnt[sl[k]], 1u);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) since[k] = add_row(v.v[k], c.v[k], sl[k]);
-    }
-    bool any_hot = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) any_hot |= (sl[k] >= 0 && since[k] >= kHotAdds - 1);
-    if (any_hot) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (sl[k] >= 0 && since[k] >= kHotAdds - 1) drain(sl[k]);
+    const unsigned seen = atomicAdd(&scnt[sl], 1u);
+    if ((seen & (kDrainEvery - 1)) == kDrainEvery - 1) {
+      // atomicExch hands the partial to exactly one thread; concurrent adds land in the fresh zero
+      const float part = atomicExch(&spart[sl], 0.0f);
+      atomicAdd(&sacc[sl], (double)part);
     }
   };
 
-  // Software pipeline over tiles of THREADS*4 rows: the 128-bit loads of tile t+1 are in flight while the
-  // atomics of tile t run (ncu r01: the first use of a loaded register was the top stall).
   struct Tile {
     const float* vals;
     const CT* codes;
     int64_t rows;
     bool full;
   };
+  int ch = 0;  // tiles are visited in increasing order: the chunk index only ever moves forward
   auto locate = [&](int64_t tile) -> Tile {
-    const int ch = find_chunk(tab, tile);
+    while (tile >= tab.tile_prefix[ch + 1]) ++ch;
     const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
     const int64_t n = tab.n[ch];
     Tile t;
@@ -318,25 +258,19 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
     }
     if (cur.full) {
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) process4(v_cur[it], c_cur[it]);
-    } else {
-      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) {
-        int sl;
-        const unsigned since = add_row(cur.vals[i], cur.codes[i], sl);
-        if (sl >= 0 && since >= kHotAdds - 1) drain(sl);
+      for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) add_row(v_cur[it].v[k], c_cur[it].v[k]);
       }
+    } else {
+      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) add_row(cur.vals[i], cur.codes[i]);
     }
     if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile loop depends on blockIdx only
       since_sweep = 0;
       __syncthreads();
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
-        const unsigned c = scnt[sl];
-        if (c) {
-          sacc[sl] += (double)spart[sl];
-          spart[sl] = 0.0f;
-          stot[sl] += c;
-          scnt[sl] = 0u;
-        }
+        sacc[sl] += (double)spart[sl];
+        spart[sl] = 0.0f;
       }
       __syncthreads();
     }
@@ -356,7 +290,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
 #pragma unroll 4
     for (int r = 0; r < R; ++r) {
       const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotated: conflict-free across the warp
-      const unsigned cs = scnt[s] + stot[s];
+      const unsigned cs = scnt[s];
       if (cs) {
         tot += sacc[s] + (double)spart[s];
         c += cs;
@@ -383,9 +317,12 @@ k_moments_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int6
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
     const VT* __restrict__ row = vals + a * row_len;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
-      int64_t i, b;
-      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
+    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
+    const int64_t di = stride / B, db = stride - (stride / B) * B;
+    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
+      if (b >= B) { b -= B; ++i; }
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
@@ -512,7 +449,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   }
   if (nbins == 0) return FLOXB_OK;
   constexpr bool kTwoLevel = std::is_same<VT, float>::value && OP != FLOXB_OP_PROD;
-  const size_t smem = kTwoLevel ? (size_t)G * 20 + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
+  const size_t smem = kTwoLevel ? (size_t)G * 16 + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
   bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
   if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
@@ -524,11 +461,10 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     KernT kern;
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
-      static const bool batch = [] { const char* e = getenv("FLOXB_F32_BATCH"); return e ? e[0] != '0' : true; }();
-      auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
-      kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, false>;
-      if (bytes(32) <= kSmemBudget) { kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, false>; smem_used = bytes(32); }
-      else if (bytes(8) <= kSmemBudget) { kern = batch ? k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, true> : k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, false>; smem_used = bytes(8); }
+      auto bytes = [&](int r) { return (size_t)G * r * 16 + (size_t)((G + 31) / 32) * 4; };
+      kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0>;
+      if (bytes(32) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5>; smem_used = bytes(32); }
+      else if (bytes(8) <= kSmemBudget) { kern = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3>; smem_used = bytes(8); }
     } else {
       kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 0>;
       if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = smem * 32; }
@@ -623,7 +559,7 @@ extern "C" int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int 
 
 extern "C" int64_t floxb_smem_group_limit(int value_dtype, int family) {
   // family 0: f32 sums use the two-level kernel (20 B / group), everything else one 64-bit slot
-  const size_t per = (family == 0) ? (value_dtype == FLOXB_F32 ? 20 : (8 + 4 + (value_dtype == FLOXB_F64 ? 4 : 0)))
+  const size_t per = (family == 0) ? (value_dtype == FLOXB_F32 ? 17 : (8 + 4 + (value_dtype == FLOXB_F64 ? 4 : 0)))
                                    : (((value_dtype == FLOXB_F32 || value_dtype == FLOXB_I32) ? 4 : 8) + 4 + 4);
   return (int64_t)(kSmemBudget / per);
 }

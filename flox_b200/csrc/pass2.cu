@@ -106,9 +106,12 @@ k_sqdev_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
     const VT* __restrict__ row = vals + a * row_len;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
-      int64_t i, b;
-      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
+    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
+    const int64_t di = stride / B, db = stride - (stride / B) * B;
+    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
+      if (b >= B) { b -= B; ++i; }
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
@@ -130,9 +133,12 @@ k_argext_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
     const VT* __restrict__ row = vals + a * row_len;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < row_len; j += stride) {
-      int64_t i, b;
-      if (B == 1) { i = j; b = 0; } else { i = j / B; b = j - i * B; }
+    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
+    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
+    const int64_t di = stride / B, db = stride - (stride / B) * B;
+    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
+      if (b >= B) { b -= B; ++i; }
       const CT c = codes[i];
       if ((unsigned long long)c >= (unsigned long long)G) continue;
       const VT v = row[j];
