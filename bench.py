@@ -143,40 +143,83 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks + throttle reasons DURING the timed region.  NVML in-process (a light query every 20 ms from
+    a daemon thread); an `nvidia-smi -lms` child process — the B200_PROFILING.md recipe — is only the fallback,
+    because its start-up and polling take driver locks that stalled launches inside short timed regions."""
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self._stop, self._thread, self.proc = index, [], False, None, None
+        self.how = None
+
+    def _nvml_loop(self, pynvml, handle):
+        reasons = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown,
+                   "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                   "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown,
+                   "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((float(sm), [k for k, bit in reasons.items() if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES remapping
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._nvml_loop, args=(pynvml, handle), daemon=True)
+            self._thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
+            self.sm_max = None
+            self._thread = threading.Thread(target=self._smi_loop, daemon=True)
+            self._thread.start()
+            self.how = "nvidia-smi"
         except OSError:
             self.proc = None
 
-    def _pump(self):
+    def _smi_loop(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 6 and c[0].replace(".", "").isdigit():
+                self.sm_max = float(c[1]) if c[1].replace(".", "").isdigit() else self.sm_max
+                self.samples.append((float(c[0]), [n for n, v in zip(names, c[2:6]) if v.lower().startswith("active")]))
+
+    @property
+    def rows(self):
+        return self.samples
+
+    def mark(self):
+        """Forget what was sampled so far (call right before the timed region)."""
+        self.samples = []
 
     def stop(self):
+        self._stop = True
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.25)
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                    if r[col].lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        elif self._thread is not None:
+            self._thread.join(timeout=1.0)
+        sm = [s for s, _ in self.samples]
+        reasons = sorted({r for _, rs in self.samples for r in rs})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": getattr(self, "sm_max", None),
+                "reasons": reasons, "samples": len(sm), "how": self.how}
 
 
 def hbm_peak():
@@ -256,6 +299,8 @@ def run_gpu(args):
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumtime").print_stats(35)
     barrier()
+    if rank == 0:
+        sampler.mark()
     l0 = k.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -266,7 +311,6 @@ def run_gpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = k.kernel_launches - l0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +338,7 @@ def run_gpu(args):
         b.synchronize()
         kt.append(a.elapsed_time(b))
     kernel_ms = float(np.mean(kt))
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed steps and the kernel-only loop
     peak, peak_src = hbm_peak()
     achieved = BYTES_PER_ROW * launch_rows / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
