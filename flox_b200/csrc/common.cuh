@@ -163,6 +163,87 @@ __device__ __forceinline__ int find_chunk(const ChunkTable& t, int64_t tile) {
   return lo;
 }
 
+// Persistent, software-pipelined walk over the tiles (THREADS*4 rows each) of a chunk table: CTA b visits
+// tiles b, b + gridDim.x, ... ; the 128-bit loads of the NEXT tile are in flight while `add_row(value, code)`
+// runs on the current one (register double buffering), and the chunk index only moves forward (no per-tile
+// binary search).  `after_tile()` runs once per tile, uniformly across the CTA (it may contain barriers).
+// Partial or unaligned tiles take a scalar path.
+template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
+__device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_tiles, AddRow add_row, AfterTile after_tile) {
+  constexpr int TILE = THREADS * 4;
+  struct Tile {
+    const VT* vals;
+    const CT* codes;
+    int64_t rows;
+    bool full;
+  };
+  int ch = 0;
+  auto locate = [&](int64_t tile) -> Tile {
+    while (tile >= tab.tile_prefix[ch + 1]) ++ch;
+    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
+    const int64_t n = tab.n[ch];
+    Tile t;
+    t.vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
+    t.codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
+    t.rows = (n - base < TILE) ? (n - base) : TILE;
+    t.full = t.rows == TILE && ((reinterpret_cast<uintptr_t>(t.vals) | reinterpret_cast<uintptr_t>(t.codes)) & 15) == 0;
+    return t;
+  };
+  // One elected thread per CTA additionally asks L2 for the tile kPrefetchTiles ahead with a bulk prefetch
+  // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2): the register prefetch one tile ahead then hits L2 instead
+  // of paying DRAM latency (ncu r01: the first use of a loaded register was still 28% of the stall samples).
+  constexpr int kPrefetchTiles = 3;
+  int pf_ch = 0;
+  auto prefetch_l2 = [&](int64_t t) {
+    if (threadIdx.x != 0 || t >= total_tiles) return;
+    while (t >= tab.tile_prefix[pf_ch + 1]) ++pf_ch;
+    const int64_t base = (t - tab.tile_prefix[pf_ch]) * TILE;
+    const int64_t rows = (tab.n[pf_ch] - base < TILE) ? (tab.n[pf_ch] - base) : TILE;
+    const VT* pv = reinterpret_cast<const VT*>(tab.values[pf_ch]) + base;
+    const CT* pc = reinterpret_cast<const CT*>(tab.codes[pf_ch]) + base;
+    const unsigned bv = (unsigned)((rows * sizeof(VT)) & ~(size_t)15), bc = (unsigned)((rows * sizeof(CT)) & ~(size_t)15);
+    if (((reinterpret_cast<uintptr_t>(pv) | reinterpret_cast<uintptr_t>(pc)) & 15) == 0 && bv && bc) {
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pv), "r"(bv) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(bc) : "memory");
+    }
+  };
+  Vec4<VT> v_cur, v_nxt;
+  Vec4<CT> c_cur, c_nxt;
+  int64_t tile = blockIdx.x;
+  for (int d = 1; d < kPrefetchTiles; ++d) prefetch_l2(tile + (int64_t)d * gridDim.x);
+  Tile cur{};
+  if (tile < total_tiles) {
+    cur = locate(tile);
+    if (cur.full) {
+      v_cur = load4<VT>(cur.vals + threadIdx.x * 4);
+      c_cur = load4<CT>(cur.codes + threadIdx.x * 4);
+    }
+  }
+  while (tile < total_tiles) {
+    const int64_t next = tile + gridDim.x;
+    prefetch_l2(tile + (int64_t)kPrefetchTiles * gridDim.x);
+    Tile nxt{};
+    if (next < total_tiles) {
+      nxt = locate(next);
+      if (nxt.full) {
+        v_nxt = load4<VT>(nxt.vals + threadIdx.x * 4);
+        c_nxt = load4<CT>(nxt.codes + threadIdx.x * 4);
+      }
+    }
+    if (cur.full) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add_row(v_cur.v[k], c_cur.v[k]);
+    } else {
+      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) add_row(cur.vals[i], cur.codes[i]);
+    }
+    after_tile();
+    cur = nxt;
+    v_cur = v_nxt;
+    c_cur = c_nxt;
+    tile = next;
+  }
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -48,32 +48,7 @@ k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G
     }
   };
 
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int ch = find_chunk(tab, tile);
-    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
-    const int64_t n = tab.n[ch];
-    const VT* __restrict__ vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
-    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
-    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
-    if (rows == TILE && aligned) {
-      Vec4<VT> v[ITERS];
-      Vec4<CT> c[ITERS];
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int off = (it * THREADS + threadIdx.x) * 4;
-        v[it] = load4<VT>(vals + off);
-        c[it] = load4<CT>(codes + off);
-      }
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
-      }
-    } else {
-      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
-    }
-  }
+  walk_tiles<VT, CT, THREADS>(tab, total_tiles, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -134,7 +109,7 @@ __global__ void k_fill_key(long long* key, unsigned long long* cnt, unsigned lon
 }
 
 constexpr int kMMThreads = 1024;
-constexpr int kMMIters = 2;
+constexpr int kMMIters = 1;
 constexpr size_t kMMSmemBudget = 227 * 1024;
 
 template <typename VT, typename CT, bool IS_MAX>

@@ -99,32 +99,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
     }
   };
 
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int ch = find_chunk(tab, tile);
-    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
-    const int64_t n = tab.n[ch];
-    const VT* __restrict__ vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
-    const CT* __restrict__ codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
-    const int64_t rows = (n - base < TILE) ? (n - base) : TILE;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(vals) | reinterpret_cast<uintptr_t>(codes)) & 15) == 0;
-    if (rows == TILE && aligned) {
-      Vec4<VT> v[ITERS];
-      Vec4<CT> c[ITERS];
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int off = (it * THREADS + threadIdx.x) * 4;
-        v[it] = load4<VT>(vals + off);
-        c[it] = load4<CT>(codes + off);
-      }
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) accum(v[it].v[k], c[it].v[k]);
-      }
-    } else {
-      for (int64_t i = threadIdx.x; i < rows; i += THREADS) accum(vals[i], codes[i]);
-    }
-  }
+  walk_tiles<VT, CT, THREADS>(tab, total_tiles, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -211,61 +186,9 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
     }
   };
 
-  struct Tile {
-    const float* vals;
-    const CT* codes;
-    int64_t rows;
-    bool full;
-  };
-  int ch = 0;  // tiles are visited in increasing order: the chunk index only ever moves forward
-  auto locate = [&](int64_t tile) -> Tile {
-    while (tile >= tab.tile_prefix[ch + 1]) ++ch;
-    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
-    const int64_t n = tab.n[ch];
-    Tile t;
-    t.vals = reinterpret_cast<const float*>(tab.values[ch]) + base;
-    t.codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
-    t.rows = (n - base < TILE) ? (n - base) : TILE;
-    t.full = t.rows == TILE && ((reinterpret_cast<uintptr_t>(t.vals) | reinterpret_cast<uintptr_t>(t.codes)) & 15) == 0;
-    return t;
-  };
-  Vec4<float> v_cur[ITERS], v_nxt[ITERS];
-  Vec4<CT> c_cur[ITERS], c_nxt[ITERS];
-  auto fetch = [&](const Tile& t, Vec4<float>* v, Vec4<CT>* c) {
-    if (t.full) {
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int off = (it * THREADS + threadIdx.x) * 4;
-        v[it] = load4<float>(t.vals + off);
-        c[it] = load4<CT>(t.codes + off);
-      }
-    }
-  };
-
   int since_sweep = 0;
-  int64_t tile = blockIdx.x;
-  Tile cur{};
-  if (tile < total_tiles) {
-    cur = locate(tile);
-    fetch(cur, v_cur, c_cur);
-  }
-  while (tile < total_tiles) {
-    const int64_t next = tile + gridDim.x;
-    Tile nxt{};
-    if (next < total_tiles) {
-      nxt = locate(next);
-      fetch(nxt, v_nxt, c_nxt);
-    }
-    if (cur.full) {
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) add_row(v_cur[it].v[k], c_cur[it].v[k]);
-      }
-    } else {
-      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) add_row(cur.vals[i], cur.codes[i]);
-    }
-    if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile loop depends on blockIdx only
+  walk_tiles<float, CT, THREADS>(tab, total_tiles, add_row, [&] {
+    if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile sequence depends on blockIdx only
       since_sweep = 0;
       __syncthreads();
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
@@ -274,14 +197,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
       }
       __syncthreads();
     }
-    cur = nxt;
-#pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      v_cur[it] = v_nxt[it];
-      c_cur[it] = c_nxt[it];
-    }
-    tile = next;
-  }
+  });
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -428,7 +344,7 @@ __global__ void k_fill_acc(AccT* acc, unsigned long long* cnt, unsigned long lon
 // host-side launchers
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemThreads = 1024;
-constexpr int kSmemIters = 2;
+constexpr int kSmemIters = 1;  // tiles of THREADS*4 rows, double-buffered by walk_tiles
 constexpr size_t kSmemBudget = 227 * 1024;
 
 template <typename VT, int OP> size_t smem_bytes_moments(int64_t G) {
@@ -455,7 +371,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   if (force_path == 2) use_smem = false;
 
   if (use_smem) {
-    constexpr int kIters = kTwoLevel ? 1 : kSmemIters;  // the two-level kernel double-buffers 4096-row tiles
+    constexpr int kIters = kSmemIters;
     constexpr int TILE = kSmemThreads * 4 * kIters;
     using KernT = void (*)(const ChunkTable, int64_t, int, AccT*, unsigned long long*, unsigned long long*);
     KernT kern;
