@@ -42,6 +42,8 @@ class CudaKernels:
         self.launches = 0  # number of C-ABI kernel entry calls issued (bench reports it)
         # testing / profiling knob: 1 = force the shared-memory path, 2 = force the L2-atomic path
         self.force_path = int(os.environ.get("FLOXB_FORCE_PATH", "0"))
+        # FLOXB_WORKSPACE=0 keeps the f64 level of the f32 shared-memory kernel in shared memory (profiling knob)
+        self.use_workspace = os.environ.get("FLOXB_WORKSPACE", "1") != "0"
         # CUDA kernel launches issued by the library (mirrors the launch logic of csrc/*.cu:
         # optional fill kernel + one launch per <=48-chunk table on the shared-memory path, or one
         # per non-empty chunk on the L2-atomic path).  bench.py reports it as `gpu_launches`.
@@ -103,9 +105,15 @@ class CudaKernels:
         self._require_cuda(acc, cnt, nnan)
         if vdt is None:
             vdt, cdt = (torch.float64 if acc.dtype == torch.float64 else torch.int64), torch.int64
-        rc = L.load().floxb_moments(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, op, self._ptr(acc),
-                                    self._ptr(cnt), self._ptr(nnan), int(init), force_path or self.force_path,
-                                    self._stream())
+        lib = L.load()
+        ws, ws_bytes = None, 0
+        if self.use_workspace and (force_path or self.force_path) != 2:
+            ws_bytes = int(lib.floxb_moments_workspace_bytes(dtype_code(vdt), A, B, G))
+            if ws_bytes:
+                ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=acc.device)  # caching allocator: no cudaMalloc
+        rc = lib.floxb_moments(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, op, self._ptr(acc),
+                               self._ptr(cnt), self._ptr(nnan), int(init), force_path or self.force_path,
+                               self._ptr(ws), ws_bytes, self._stream())
         L.check(rc, "floxb_moments")
         self.launches += 1
         self._scan_launches(chunks, A, B, G, init, 0, vdt, force_path or self.force_path)

@@ -89,10 +89,17 @@ int64_t floxb_smem_group_limit(int value_dtype, int family /*0 moments, 1 minmax
  *              (an exact NaN count on the L2-atomic and column paths, the number of CTAs that saw a
  *              NaN on the shared-memory f32 path)
  *   init       1 = reset the accumulators first (0 / 1 for PROD), 0 = accumulate on top
- *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics (testing / profiling) */
+ *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics (testing / profiling)
+ *   workspace  optional scratch, see floxb_moments_workspace_bytes */
 int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
                   int64_t A, int64_t B, int64_t n_groups, int op, void* acc, int64_t* cnt,
-                  int64_t* nnan, int init, int force_path, void* stream);
+                  int64_t* nnan, int init, int force_path, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+/* Optional scratch for floxb_moments (device memory, need not be initialised, may be NULL): with at least
+ * this many bytes the f32 shared-memory kernel keeps its f64 level in L2-resident global memory instead of
+ * shared memory (8 instead of 16 bytes of shared memory per group -> more L1 for the streaming loads, and
+ * twice the groups fit).  0 = the call has no use for a workspace.  Must not be shared by concurrent calls. */
+int64_t floxb_moments_workspace_bytes(int value_dtype, int64_t A, int64_t B, int64_t n_groups);
 
 /* Grouped max / min of the non-NaN values as order-preserving i64 keys, plus the counts.
  * Replaces aggregate_flox.max/min/nanmax/nanmin (flox/aggregate_flox.py:214-217,195-207).

@@ -37,7 +37,9 @@ def test_library_exports_every_declared_symbol():
 def test_argument_validation_without_gpu():
     lib = _lib.load()
     # invalid arguments are rejected before any CUDA call
-    assert lib.floxb_moments(None, -1, 0, 3, 1, 1, 4, 0, None, None, None, 1, 0, None) == -1
+    assert lib.floxb_moments(None, -1, 0, 3, 1, 1, 4, 0, None, None, None, 1, 0, None, 0, None) == -1
+    assert lib.floxb_moments_workspace_bytes(_lib.F32, 1, 1, 100) == 0  # small G: replicated slots, no workspace
+    assert lib.floxb_moments_workspace_bytes(_lib.F64, 1, 1, 10_000) == 0
     assert lib.floxb_combine(0, 0, None, 0, 4, None, None) == -1
     assert lib.floxb_smem_group_limit(_lib.F32, 0) >= 10_000
 

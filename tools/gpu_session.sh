@@ -19,7 +19,7 @@ bench)
   timeout 900 python bench.py --steps 20 --warmup 3 --profile-host > gpurun_out/bench.log 2> gpurun_out/bench_hostprofile.log; echo "bench rc=$?" >> gpurun_out/bench.log ;;
 benchab)
   for b in 1 0; do
-    FLOXB_F32_BATCH=$b timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_batch$b.log 2>&1
+    FLOXB_WORKSPACE=$b timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_ws$b.log 2>&1
   done ;;
 kbench2)
   timeout 600 python tools/kbench2.py > gpurun_out/kbench2.log 2>&1 ;;
