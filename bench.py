@@ -298,6 +298,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
         prof.disable()
         pstats.Stats(prof, stream=sys.stderr).sort_stats("cumtime").print_stats(35)
+    # Spin-up (untimed, in addition to the W warm-up steps): keep the GPU busy for ~0.3 s (100 steps) so that the timed
+    # region starts in steady state.  Waiting for the clock sampler above idles the device, and the first
+    # ~20 steps after an idle gap ran 1.6x slower than steady state (profiles/r01: 5.2 vs 3.2 ms/step).
+    for _ in range(100):  # a FIXED count: every rank must issue the same number of collectives
+        step()
     barrier()
     if rank == 0:
         sampler.mark()

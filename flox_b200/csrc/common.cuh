@@ -192,7 +192,7 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_
   // One elected thread per CTA additionally asks L2 for the tile kPrefetchTiles ahead with a bulk prefetch
   // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2): the register prefetch one tile ahead then hits L2 instead
   // of paying DRAM latency (ncu r01: the first use of a loaded register was still 28% of the stall samples).
-  constexpr int kPrefetchTiles = 3;
+  constexpr int kPrefetchTiles = 4;
   int pf_ch = 0;
   auto prefetch_l2 = [&](int64_t t) {
     if (threadIdx.x != 0 || t >= total_tiles) return;
@@ -207,40 +207,52 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(bc) : "memory");
     }
   };
-  Vec4<VT> v_cur, v_nxt;
-  Vec4<CT> c_cur, c_nxt;
+  // Register pipeline two tiles deep: three statically named buffers rotate through load -> wait -> process.
+  Vec4<VT> vb[3];
+  Vec4<CT> cb[3];
+  Tile tb[3];
+  const int64_t step = gridDim.x;
   int64_t tile = blockIdx.x;
-  for (int d = 1; d < kPrefetchTiles; ++d) prefetch_l2(tile + (int64_t)d * gridDim.x);
-  Tile cur{};
-  if (tile < total_tiles) {
-    cur = locate(tile);
-    if (cur.full) {
-      v_cur = load4<VT>(cur.vals + threadIdx.x * 4);
-      c_cur = load4<CT>(cur.codes + threadIdx.x * 4);
-    }
-  }
-  while (tile < total_tiles) {
-    const int64_t next = tile + gridDim.x;
-    prefetch_l2(tile + (int64_t)kPrefetchTiles * gridDim.x);
-    Tile nxt{};
-    if (next < total_tiles) {
-      nxt = locate(next);
-      if (nxt.full) {
-        v_nxt = load4<VT>(nxt.vals + threadIdx.x * 4);
-        c_nxt = load4<CT>(nxt.codes + threadIdx.x * 4);
+  for (int d = 2; d <= kPrefetchTiles; ++d) prefetch_l2(tile + (int64_t)d * step);
+  auto issue = [&](int slot, int64_t t) {
+    tb[slot] = Tile{};
+    if (t < total_tiles) {
+      tb[slot] = locate(t);
+      if (tb[slot].full) {
+        vb[slot] = load4<VT>(tb[slot].vals + threadIdx.x * 4);
+        cb[slot] = load4<CT>(tb[slot].codes + threadIdx.x * 4);
       }
     }
-    if (cur.full) {
+  };
+  auto consume = [&](int slot) {
+    if (tb[slot].full) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) add_row(v_cur.v[k], c_cur.v[k]);
+      for (int k = 0; k < 4; ++k) add_row(vb[slot].v[k], cb[slot].v[k]);
     } else {
-      for (int64_t i = threadIdx.x; i < cur.rows; i += THREADS) add_row(cur.vals[i], cur.codes[i]);
+      for (int64_t i = threadIdx.x; i < tb[slot].rows; i += THREADS) add_row(tb[slot].vals[i], tb[slot].codes[i]);
     }
     after_tile();
-    cur = nxt;
-    v_cur = v_nxt;
-    c_cur = c_nxt;
-    tile = next;
+  };
+  issue(0, tile);
+  issue(1, tile + step);
+  while (tile < total_tiles) {
+    // sub-step A: load slot 2, process slot 0
+    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
+    issue(2, tile + 2 * step);
+    consume(0);
+    tile += step;
+    if (tile >= total_tiles) break;
+    // sub-step B: load slot 0, process slot 1
+    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
+    issue(0, tile + 2 * step);
+    consume(1);
+    tile += step;
+    if (tile >= total_tiles) break;
+    // sub-step C: load slot 1, process slot 2
+    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
+    issue(1, tile + 2 * step);
+    consume(2);
+    tile += step;
   }
 }
 

@@ -143,7 +143,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
 // The tile loop is software-pipelined (loads of tile t+1 in flight during the atomics of tile t) and walks
 // the chunk table monotonically (no per-tile binary search): tools/kbench.py v22 vs v9.
-constexpr int kSweepTiles = 16;  // tiles of THREADS*4*ITERS rows (4096 with ITERS = 1)
+constexpr int kSweepTiles = 24;  // tiles of THREADS*4 rows: ~10 adds per slot between sweeps at G = 1e4
 constexpr unsigned kDrainEvery = 32;  // power of two
 
 // WS: level 2 lives in a caller-provided, CTA-private slice of GLOBAL memory (L2-resident: 148 x G x 8 B)
