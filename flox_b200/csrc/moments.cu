@@ -143,7 +143,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
 // The tile loop is software-pipelined (loads of tile t+1 in flight during the atomics of tile t) and walks
 // the chunk table monotonically (no per-tile binary search): tools/kbench.py v22 vs v9.
-constexpr int kSweepTiles = 24;  // tiles of THREADS*4 rows: ~10 adds per slot between sweeps at G = 1e4
+constexpr int kSweepTiles = 32;  // tiles of THREADS*4 rows: ~13 adds per slot between sweeps at G = 1e4
 constexpr unsigned kDrainEvery = 32;  // power of two
 
 // WS: level 2 lives in a caller-provided, CTA-private slice of GLOBAL memory (L2-resident: 148 x G x 8 B)
@@ -161,13 +161,18 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   const int S = G << RSHIFT;
   const int NW = (G + 31) >> 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sacc = WS ? workspace + (size_t)blockIdx.x * S : reinterpret_cast<double*>(smem_raw);  // [S] level 2 sum
-  float* spart = reinterpret_cast<float*>(smem_raw + (WS ? 0 : (size_t)S * 8));                   // [S] level 1 partial
-  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);   // [S] number of adds
+  // level 2 (sum f64 + adds before the last sweep u32): workspace slice [S f64][S u32] or shared memory
+  const size_t ws_stride = (size_t)S * 8 + (((size_t)S * 4 + 7) & ~(size_t)7);  // keep every slice 8-byte aligned
+  double* sacc = WS ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)blockIdx.x * ws_stride)
+                    : reinterpret_cast<double*>(smem_raw);
+  unsigned* stot = WS ? reinterpret_cast<unsigned*>(sacc + S) : reinterpret_cast<unsigned*>(smem_raw + (size_t)S * 8);
+  float* spart = reinterpret_cast<float*>(smem_raw + (WS ? 0 : (size_t)S * 12));  // [S] level 1 partial
+  unsigned* scnt = reinterpret_cast<unsigned*>(spart + S);   // [S] adds since the last sweep
   unsigned* snanbits = scnt + S;                              // [NW] group-has-NaN flags
   const int copy = threadIdx.x & (R - 1);
   for (int s = threadIdx.x; s < S; s += THREADS) {
     sacc[s] = 0.0;
+    stot[s] = 0u;
     spart[s] = 0.0f;
     scnt[s] = 0u;
   }
@@ -185,10 +190,13 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
     const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
     atomicAdd(&spart[sl], w);
     const unsigned seen = atomicAdd(&scnt[sl], 1u);
-    if ((seen & (kDrainEvery - 1)) == kDrainEvery - 1) {
-      // atomicExch hands the partial to exactly one thread; concurrent adds land in the fresh zero
+    if (seen >= kDrainEvery - 1) {
+      // hot slot (kDrainEvery adds since the last sweep): hand partial and counter to level 2 now.  atomicExch
+      // gives each to exactly one thread; concurrent adds land in the fresh zeros.  Never taken for evenly
+      // spread groups (~10 adds per slot between sweeps), every kDrainEvery-th add for a hot group.
       const float part = atomicExch(&spart[sl], 0.0f);
       atomicAdd(&sacc[sl], (double)part);
+      atomicAdd(&stot[sl], atomicExch(&scnt[sl], 0u));
     }
   };
 
@@ -198,8 +206,13 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
       since_sweep = 0;
       __syncthreads();
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
-        sacc[sl] += (double)spart[sl];
-        spart[sl] = 0.0f;
+        const unsigned c = scnt[sl];
+        if (c) {
+          sacc[sl] += (double)spart[sl];
+          spart[sl] = 0.0f;
+          stot[sl] += c;
+          scnt[sl] = 0u;
+        }
       }
       __syncthreads();
     }
@@ -212,7 +225,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
 #pragma unroll 4
     for (int r = 0; r < R; ++r) {
       const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotated: conflict-free across the warp
-      const unsigned cs = scnt[s];
+      const unsigned cs = scnt[s] + stot[s];
       if (cs) {
         tot += sacc[s] + (double)spart[s];
         c += cs;
@@ -372,8 +385,8 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   }
   if (nbins == 0) return FLOXB_OK;
   constexpr bool kTwoLevel = std::is_same<VT, float>::value && OP != FLOXB_OP_PROD;
-  const bool use_ws = kTwoLevel && workspace != nullptr && workspace_bytes >= (int64_t)sm_count() * G * 8;
-  const size_t smem = kTwoLevel ? (size_t)G * (use_ws ? 8 : 16) + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
+  const bool use_ws = kTwoLevel && workspace != nullptr && workspace_bytes >= (int64_t)sm_count() * (G * 12 + 8);
+  const size_t smem = kTwoLevel ? (size_t)G * (use_ws ? 8 : 20) + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
   bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
   if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
@@ -387,7 +400,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     KernWsT kern_ws = nullptr;
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
-      auto bytes = [&](int r) { return (size_t)G * r * 16 + (size_t)((G + 31) / 32) * 4; };
+      auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
       if (bytes(32) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, false>; smem_used = bytes(32); }
       else if (bytes(8) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, false>; smem_used = bytes(8); }
       else if (use_ws) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, true>; }
@@ -495,9 +508,9 @@ extern "C" int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int 
 extern "C" int64_t floxb_moments_workspace_bytes(int value_dtype, int64_t A, int64_t B, int64_t n_groups) {
   // only the two-level f32 kernel with one slot copy per group (G too large for replicated slots) uses it
   if (value_dtype != FLOXB_F32 || A != 1 || B != 1) return 0;
-  if ((size_t)n_groups * 8 * 16 + 64 <= kSmemBudget) return 0;          // replicated slots: level 2 stays in smem
+  if ((size_t)n_groups * 8 * 20 + 64 <= kSmemBudget) return 0;          // replicated slots: level 2 stays in smem
   if ((size_t)n_groups * 8 + (size_t)((n_groups + 31) / 32) * 4 > kSmemBudget) return 0;  // L2-atomic path
-  return (int64_t)sm_count() * n_groups * 8;
+  return (int64_t)sm_count() * (n_groups * 12 + 8);
 }
 
 extern "C" int64_t floxb_smem_group_limit(int value_dtype, int family) {

@@ -110,7 +110,7 @@ class CudaKernels:
         if self.use_workspace and (force_path or self.force_path) != 2:
             ws_bytes = int(lib.floxb_moments_workspace_bytes(dtype_code(vdt), A, B, G))
             if ws_bytes:
-                ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=acc.device)  # caching allocator: no cudaMalloc
+                ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=acc.device)  # caching allocator: no cudaMalloc
         rc = lib.floxb_moments(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, op, self._ptr(acc),
                                self._ptr(cnt), self._ptr(nnan), int(init), force_path or self.force_path,
                                self._ptr(ws), ws_bytes, self._stream())
