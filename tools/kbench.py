@@ -33,7 +33,7 @@ def main():
     x = torch.rand(n, device="cuda", generator=gen)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     VARIANTS = [int(v) for v in os.environ.get("KBENCH_VARIANTS", ",".join(map(str, range(26)))).split(",")]
-    for G in (10_000, 100, 1000):
+    for G in [int(g) for g in os.environ.get("KBENCH_GROUPS", "10000,100,1000").split(",")]:
         by = torch.randint(0, G, (n,), device="cuda", generator=gen, dtype=torch.int64)
         acc = torch.zeros(G, dtype=torch.float64, device="cuda")
         cnt = torch.zeros(G, dtype=torch.int64, device="cuda")
