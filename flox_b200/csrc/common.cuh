@@ -168,7 +168,7 @@ __device__ __forceinline__ int find_chunk(const ChunkTable& t, int64_t tile) {
 // runs on the current one (register double buffering), and the chunk index only moves forward (no per-tile
 // binary search).  `after_tile()` runs once per tile, uniformly across the CTA (it may contain barriers).
 // Partial or unaligned tiles take a scalar path.
-template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
+template <typename VT, typename CT, int THREADS, int kPrefetchTiles = 4, typename AddRow, typename AfterTile>
 __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_tiles, AddRow add_row, AfterTile after_tile) {
   constexpr int TILE = THREADS * 4;
   struct Tile {
@@ -192,10 +192,9 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_
   // One elected thread per CTA additionally asks L2 for the tile kPrefetchTiles ahead with a bulk prefetch
   // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2): the register prefetch one tile ahead then hits L2 instead
   // of paying DRAM latency (ncu r01: the first use of a loaded register was still 28% of the stall samples).
-  constexpr int kPrefetchTiles = 4;
   int pf_ch = 0;
   auto prefetch_l2 = [&](int64_t t) {
-    if (threadIdx.x != 0 || t >= total_tiles) return;
+    if (kPrefetchTiles == 0 || threadIdx.x != 0 || t >= total_tiles) return;
     while (t >= tab.tile_prefix[pf_ch + 1]) ++pf_ch;
     const int64_t base = (t - tab.tile_prefix[pf_ch]) * TILE;
     const int64_t rows = (tab.n[pf_ch] - base < TILE) ? (tab.n[pf_ch] - base) : TILE;

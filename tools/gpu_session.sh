@@ -24,6 +24,8 @@ benchab)
 ncukexp)
   KBENCH_VARIANTS=22 KBENCH_GROUPS=10000 timeout 600 ncu --set full --clock-control none -k regex:k_exp_pipe -s 1 -c 1 -f -o gpurun_out/prof_kexp22 \
       python tools/kbench.py 268435456 > gpurun_out/ncu_kexp.log 2>&1 ;;
+kbench3)
+  timeout 600 python tools/kbench3.py > gpurun_out/kbench3.log 2>&1 ;;
 kbench2)
   timeout 600 python tools/kbench2.py > gpurun_out/kbench2.log 2>&1 ;;
 configs)
