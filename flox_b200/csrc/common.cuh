@@ -255,6 +255,64 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_
   }
 }
 
+// Lean variant of the persistent walk (tools/kbench3.py: the three-buffer walk above costs 6-11 points of
+// HBM roofline against a bare two-buffer loop).  The hot loop only ever sees FULL, 16-byte-aligned tiles:
+// CTA b takes every gridDim.x-th full tile of the concatenated chunks (the round-robin position carries over
+// chunk boundaries, so the load stays balanced), with the 128-bit loads of its next tile in flight while
+// `add_row(value, code)` runs on the current one.  Chunk tails (n % TILE rows) and unaligned chunks are
+// handled afterwards by a scalar loop, spread over the CTAs.  `after_tile()` runs once per full tile.
+template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
+__device__ __forceinline__ void walk_tiles2(const ChunkTable& tab, AddRow add_row, AfterTile after_tile) {
+  constexpr int TILE = THREADS * 4;
+  const int nch = tab.nchunks;
+  auto full_tiles = [&](int k) -> int64_t {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(tab.values[k]) | reinterpret_cast<uintptr_t>(tab.codes[k])) & 15) == 0;
+    return aligned ? tab.n[k] / TILE : 0;
+  };
+  int ch = 0;
+  int64_t local = blockIdx.x, ft = nch > 0 ? full_tiles(0) : 0;
+  auto settle = [&] {
+    while (ch < nch && local >= ft) {
+      local -= ft;
+      if (++ch < nch) ft = full_tiles(ch);
+    }
+  };
+  settle();
+  Vec4<VT> v0, v1;
+  Vec4<CT> c0, c1;
+  bool have = ch < nch;
+  if (have) {
+    v0 = load4<VT>(reinterpret_cast<const VT*>(tab.values[ch]) + local * TILE + threadIdx.x * 4);
+    c0 = load4<CT>(reinterpret_cast<const CT*>(tab.codes[ch]) + local * TILE + threadIdx.x * 4);
+  }
+  while (have) {
+    local += gridDim.x;
+    settle();
+    have = ch < nch;
+    if (have) {
+      v1 = load4<VT>(reinterpret_cast<const VT*>(tab.values[ch]) + local * TILE + threadIdx.x * 4);
+      c1 = load4<CT>(reinterpret_cast<const CT*>(tab.codes[ch]) + local * TILE + threadIdx.x * 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) add_row(v0.v[k], c0.v[k]);
+    after_tile();
+    v0 = v1;
+    c0 = c1;
+  }
+  // scalar leftovers: piece j of chunk k goes to CTA (k + j) mod gridDim.x
+  for (int k = 0; k < nch; ++k) {
+    const VT* vals = reinterpret_cast<const VT*>(tab.values[k]);
+    const CT* codes = reinterpret_cast<const CT*>(tab.codes[k]);
+    const int64_t start = full_tiles(k) * TILE, n = tab.n[k];
+    int64_t j = ((int64_t)blockIdx.x - k) % (int64_t)gridDim.x;
+    if (j < 0) j += gridDim.x;
+    for (int64_t base = start + j * TILE; base < n; base += (int64_t)gridDim.x * TILE) {
+      const int64_t end = (n - base < TILE) ? n : base + TILE;
+      for (int64_t i = base + threadIdx.x; i < end; i += THREADS) add_row(vals[i], codes[i]);
+    }
+  }
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

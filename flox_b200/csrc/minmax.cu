@@ -48,7 +48,7 @@ k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G
     }
   };
 
-  walk_tiles<VT, CT, THREADS>(tab, total_tiles, accum, [] {});
+  walk_tiles2<VT, CT, THREADS>(tab, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {

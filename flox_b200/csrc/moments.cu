@@ -99,7 +99,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
     }
   };
 
-  walk_tiles<VT, CT, THREADS>(tab, total_tiles, accum, [] {});
+  walk_tiles2<VT, CT, THREADS>(tab, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -131,8 +131,9 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 //          wavefronts per 32 random rows instead of ~21 for a 64-bit slot) + a native u32 counter
 //          (ATOMS.ADD; the returned old count costs nothing extra — tools/kbench.py v24 vs v9).
 // Level 2: f64 accumulator per slot.  Level 1 moves into level 2
-//          (a) in a barrier-fenced SWEEP every kSweepTiles tiles — plain, conflict-free LDS/STS; for
-//              evenly spread groups a partial then holds ~kSweepTiles * TILE / G addends (6.6 at G = 1e4);
+//          (a) in a barrier-free SWEEP: every kSweepTiles tiles each thread atomicExch-es its own slots
+//              (conflict-free) and adds them to level 2; for evenly spread groups a partial then holds
+//              ~kSweepTiles * TILE / G addends (26 at G = 1e4);
 //          (b) immediately, by the thread whose counter value shows that the slot just completed another
 //              kDrainEvery adds (atomicExch of the partial + one 64-bit CAS), so hot or bursty groups
 //              (skewed or sorted labels) never keep more than kDrainEvery (+ racing) addends in f32.
@@ -143,11 +144,11 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
 // The tile loop is software-pipelined (loads of tile t+1 in flight during the atomics of tile t) and walks
 // the chunk table monotonically (no per-tile binary search): tools/kbench.py v22 vs v9.
-constexpr int kSweepTiles = 32;  // tiles of THREADS*4 rows: ~13 adds per slot between sweeps at G = 1e4
-constexpr unsigned kDrainEvery = 32;  // power of two
+constexpr int kSweepTiles = 64;  // tiles of THREADS*4 rows: ~26 adds per slot between sweeps at G = 1e4
+constexpr unsigned kDrainEvery = 32;  // <= this many (+ racing) addends per f32 partial, whatever the skew
 
 // WS: level 2 lives in a caller-provided, CTA-private slice of GLOBAL memory (L2-resident: 148 x G x 8 B)
-// instead of shared memory.  It is only touched by the sweeps (coalesced plain loads/stores) and the rare
+// instead of shared memory.  It is only touched by the sweeps (coalesced RED.ADD.F64 / RED.ADD.U32) and the rare
 // hot-slot drains, and it shrinks the kernel's shared-memory footprint from 16 to 8 bytes per slot — which
 // matters because the L1 that backs the streaming loads is whatever shared memory leaves over
 // (tools/kbench.py: the same loop runs 26% slower with 200 KB than with 120 KB of dynamic shared memory).
@@ -200,21 +201,22 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
     }
   };
 
+  // Barrier-free sweep: every thread hands ITS slots to level 2 with atomicExch every kSweepTiles of its own
+  // tiles.  A row racing with the sweep either lands before the exchange (moved now) or in the fresh zero
+  // (moved by the next sweep); its count may travel one sweep later than its value, which only matters to the
+  // drain heuristic.  (tools/kbench3.py: __syncthreads-fenced sweeps cost 7 points of roofline, these 2.)
   int since_sweep = 0;
-  walk_tiles<float, CT, THREADS>(tab, total_tiles, add_row, [&] {
-    if (++since_sweep == kSweepTiles) {  // uniform across the CTA: the tile sequence depends on blockIdx only
+  walk_tiles2<float, CT, THREADS>(tab, add_row, [&] {
+    if (++since_sweep == kSweepTiles) {
       since_sweep = 0;
-      __syncthreads();
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
-        const unsigned c = scnt[sl];
+        const unsigned c = atomicExch(&scnt[sl], 0u);
         if (c) {
-          sacc[sl] += (double)spart[sl];
-          spart[sl] = 0.0f;
-          stot[sl] += c;
-          scnt[sl] = 0u;
+          const float p = atomicExch(&spart[sl], 0.0f);
+          atomicAdd(&sacc[sl], (double)p);
+          atomicAdd(&stot[sl], c);
         }
       }
-      __syncthreads();
     }
   });
   __syncthreads();
@@ -225,9 +227,9 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
 #pragma unroll 4
     for (int r = 0; r < R; ++r) {
       const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));  // rotated: conflict-free across the warp
-      const unsigned cs = scnt[s] + stot[s];
+      const unsigned cs = scnt[s] + (WS ? __ldcg(&stot[s]) : stot[s]);  // level 2 was written by L2 atomics: bypass L1
       if (cs) {
-        tot += sacc[s] + (double)spart[s];
+        tot += (WS ? __ldcg(&sacc[s]) : sacc[s]) + (double)spart[s];
         c += cs;
       }
     }

@@ -226,7 +226,10 @@ def test_f32_two_level_accuracy_under_skew(ngroups):
         scale = torch.zeros(ngroups, dtype=torch.float64, device="cuda").index_add_(0, by, x.abs().to(torch.float64))
         got, _ = flox_b200.groupby_reduce(x, by, func="sum", expected_groups=np.arange(ngroups), dtype=np.float64)
         err = ((got - exact).abs() / scale).max().item()
-        assert err < 2e-7, (name, ngroups, err)   # bound is ~6e-7 of sum|x|; typical is ~1e-9
+        # every f32 partial holds <= 32 addends before it moves to f64: the error is ~sqrt(32) * 2^-25 of the
+        # partial (a strict bound of 32 * 2^-24 needs every rounding to go the same way).  Well-scaled data
+        # measure ~1e-9, the 12-decade lognormal (one huge addend dominates its partial) 2-3e-7; the bar is 1e-6.
+        assert err < 5e-7, (name, ngroups, err)
         got32, _ = flox_b200.groupby_reduce(x, by, func="mean", expected_groups=np.arange(ngroups))
         cnt = torch.bincount(by, minlength=ngroups).to(torch.float64)
         rel = ((got32.to(torch.float64) - exact / cnt).abs() / (scale / cnt)).max().item()

@@ -7,7 +7,7 @@ using namespace floxb;
 
 namespace {
 
-enum : unsigned { F_WALK = 1, F_NAN = 2, F_RET = 4, F_SWEEP = 8, F_WS = 16, F_NOPF = 32, F_PF8 = 64 };
+enum : unsigned { F_WALK = 1, F_NAN = 2, F_RET = 4, F_SWEEP = 8, F_WS = 16, F_NOPF = 32, F_PF8 = 64, F_WALK2 = 128, F_SWEEP2 = 256, F_SW64 = 512 };
 
 template <unsigned F>
 __global__ void __launch_bounds__(1024, 1)
@@ -17,9 +17,10 @@ k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const floa
   constexpr int THREADS = 1024;
   constexpr int TILE = THREADS * 4;
   constexpr bool WS = (F & F_WS) != 0;
-  constexpr bool SWEEP = (F & F_SWEEP) != 0;
-  constexpr unsigned kDrainEvery = 32;
-  constexpr int kSweepTiles = 32;
+  constexpr bool SWEEP2 = (F & F_SWEEP2) != 0;  // barrier-free sweeps (atomicExch), level 2 in the workspace
+  constexpr bool SWEEP = (F & F_SWEEP) != 0 || SWEEP2;
+  constexpr unsigned kDrainEvery = (F & F_SW64) ? 64 : 32;
+  constexpr int kSweepTiles = (F & F_SW64) ? 64 : 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int S = G;
   const size_t ws_stride = (size_t)S * 8 + (((size_t)S * 4 + 7) & ~(size_t)7);
@@ -67,7 +68,19 @@ k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const floa
   int since_sweep = 0;
   auto after_tile = [&] {
     if constexpr (SWEEP) {
-      if (++since_sweep == kSweepTiles) {
+      if (SWEEP2) {
+        if (++since_sweep == kSweepTiles) {
+          since_sweep = 0;
+          for (int sl = threadIdx.x; sl < S; sl += THREADS) {
+            const unsigned c = atomicExch(&scnt[sl], 0u);
+            if (c) {
+              const float p = atomicExch(&spart[sl], 0.0f);
+              atomicAdd(&sacc[sl], (double)p);
+              atomicAdd(&stot[sl], c);
+            }
+          }
+        }
+      } else if (++since_sweep == kSweepTiles) {
         since_sweep = 0;
         __syncthreads();
         for (int sl = threadIdx.x; sl < S; sl += THREADS) {
@@ -84,7 +97,9 @@ k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const floa
     }
   };
 
-  if constexpr ((F & F_WALK) != 0) {
+  if constexpr ((F & F_WALK2) != 0) {
+    walk_tiles2<float, int64_t, THREADS>(tab, add_row, after_tile);
+  } else if constexpr ((F & F_WALK) != 0) {
     constexpr int PF = (F & F_NOPF) ? 0 : ((F & F_PF8) ? 8 : 4);
     walk_tiles<float, int64_t, THREADS, PF>(tab, total_tiles, add_row, after_tile);
   } else {
@@ -167,6 +182,13 @@ extern "C" int kexp3_run(int variant, const float* v, const long long* c, int64_
     V(10, F_SWEEP | F_WS)
     V(11, F_NAN)
     V(12, F_RET)
+    V(13, F_WALK2)
+    V(14, F_WALK2 | F_NAN | F_RET)
+    V(15, F_WALK2 | F_NAN | F_RET | F_SWEEP | F_WS)
+    V(16, F_WALK2 | F_NAN | F_RET | F_SWEEP2 | F_WS)
+    V(17, F_NAN | F_RET | F_SWEEP2 | F_WS)
+    V(18, F_WALK2 | F_NAN | F_RET | F_SWEEP2 | F_WS | F_SW64)
+    V(19, F_WALK2 | F_NAN | F_RET | F_SWEEP | F_WS | F_SW64)
   }
   return -1;
 }
@@ -174,6 +196,8 @@ extern "C" int kexp3_run(int variant, const float* v, const long long* c, int64_
 extern "C" const char* kexp3_name(int variant) {
   static const char* names[] = {"bare pipe", "walk", "walk+nan", "walk+nan+ret", "walk+nan+ret+sweep(smem)", "walk+nan+ret+sweep(ws) = production",
                                 "bare+nan+ret+sweep(ws)", "walk, no L2 prefetch", "bare+nan+ret", "walk, L2 prefetch 8 ahead",
-                                "bare+sweep(ws)", "bare+nan", "bare+ret"};
-  return (variant >= 0 && variant < 13) ? names[variant] : "?";
+                                "bare+sweep(ws)", "bare+nan", "bare+ret", "walk2", "walk2+nan+ret", "walk2+nan+ret+sweep(ws)",
+                                "walk2+nan+ret+sweep2(ws, no barrier)", "bare+nan+ret+sweep2", "walk2+nan+ret+sweep2 every 64",
+                                "walk2+nan+ret+sweep(ws) every 64"};
+  return (variant >= 0 && variant < 20) ? names[variant] : "?";
 }
