@@ -324,8 +324,10 @@ def run_gpu(args):
     value = world * rows / (ms_per_step * 1e-3)
 
     # ---- dominant kernel alone (roofline): floxb_moments over the same 100 chunks, CUDA events
-    # one launch covers a table of up to 48 chunks (csrc/common.cuh: kMaxChunksPerLaunch); time exactly one
-    chunks = [(v.reshape(1, -1, 1), c) for v, c in zip(arr.chunks, lab.chunks)][:48]
+    # one launch covers a table of up to 128 chunks (csrc/common.cuh: kMaxChunksPerLaunch): the step's 100 chunks
+    # are exactly one launch of the dominant kernel; time that launch
+    per_launch = k.max_chunks_per_launch()
+    chunks = [(v.reshape(1, -1, 1), c) for v, c in zip(arr.chunks, lab.chunks)][:per_launch]
     launch_rows = sum(c.numel() for _, c in chunks)
     acc = torch.empty(G, dtype=torch.float64, device=dev)
     cnt = torch.empty(G, dtype=torch.int64, device=dev)
@@ -337,7 +339,7 @@ def run_gpu(args):
     kt = []
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # ~1.5 ms of device-side spinning queued first: the host builds the 48-entry chunk table and enqueues the
+        # ~1.5 ms of device-side spinning queued first: the host builds the chunk table and enqueues the
         # launch while it runs, so the interval between the two events is the kernel's duration and not the
         # host's enqueue latency on an idle GPU (~0.09 ms here, 7% of the kernel)
         torch.cuda._sleep(3_000_000)
@@ -353,7 +355,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "kernel": "k_moments_smem_f32<long,SUM,1024,1,0,WS> (floxb_moments, two-level f32 bins)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kernel_ms, "rows_per_launch": launch_rows,
-                "launches_per_step": -(-len(arr.chunks) // 48), "algorithmic_bytes_per_launch": BYTES_PER_ROW * launch_rows,
+                "launches_per_step": -(-len(arr.chunks) // per_launch), "algorithmic_bytes_per_launch": BYTES_PER_ROW * launch_rows,
                 "secondary_limit": "L1TEX shared-memory wavefronts (atomic CAS on privatised bins), see profiles/"}
 
     # ---- end to end: pinned host buffers -> public API -> host result

@@ -35,6 +35,7 @@ SIGNATURES = {
     "floxb_strerror": (C.c_char_p, [_i32]),
     "floxb_last_cuda_error": (C.c_char_p, []),
     "floxb_smem_group_limit": (_i64, [_i32, _i32]),
+    "floxb_max_chunks_per_launch": (_i32, []),
     "floxb_moments": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _i64, _vp]),
     "floxb_moments_workspace_bytes": (_i64, [_i32, _i64, _i64, _i64]),
     "floxb_minmax": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _vp]),

@@ -14,14 +14,14 @@
 
 namespace floxb {
 
-constexpr int kMaxChunksPerLaunch = 48;
+constexpr int kMaxChunksPerLaunch = 128;
 
-// Chunk table passed BY VALUE in kernel parameter space (no device allocation, no copy).
+// Chunk table passed BY VALUE in kernel parameter space (no device allocation, no copy): 3 KB of the 4 KB
+// parameter space, so BASELINE config 2's 100 chunks are ONE persistent launch.
 struct ChunkTable {
   const void* values[kMaxChunksPerLaunch];
   const void* codes[kMaxChunksPerLaunch];
-  int64_t n[kMaxChunksPerLaunch];            // reduced length of each chunk
-  int64_t tile_prefix[kMaxChunksPerLaunch + 1];  // exclusive prefix of per-chunk tile counts
+  int64_t n[kMaxChunksPerLaunch];  // reduced length of each chunk
   int nchunks;
 };
 
@@ -153,116 +153,15 @@ __device__ __forceinline__ void atomic_add(long long* a, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v);
 }
 
-// Map a flat persistent tile index onto (chunk, tile-within-chunk).
-__device__ __forceinline__ int find_chunk(const ChunkTable& t, int64_t tile) {
-  int lo = 0, hi = t.nchunks - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (t.tile_prefix[mid] <= tile) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
-
-// Persistent, software-pipelined walk over the tiles (THREADS*4 rows each) of a chunk table: CTA b visits
-// tiles b, b + gridDim.x, ... ; the 128-bit loads of the NEXT tile are in flight while `add_row(value, code)`
-// runs on the current one (register double buffering), and the chunk index only moves forward (no per-tile
-// binary search).  `after_tile()` runs once per tile, uniformly across the CTA (it may contain barriers).
-// Partial or unaligned tiles take a scalar path.
-template <typename VT, typename CT, int THREADS, int kPrefetchTiles = 4, typename AddRow, typename AfterTile>
-__device__ __forceinline__ void walk_tiles(const ChunkTable& tab, int64_t total_tiles, AddRow add_row, AfterTile after_tile) {
-  constexpr int TILE = THREADS * 4;
-  struct Tile {
-    const VT* vals;
-    const CT* codes;
-    int64_t rows;
-    bool full;
-  };
-  int ch = 0;
-  auto locate = [&](int64_t tile) -> Tile {
-    while (tile >= tab.tile_prefix[ch + 1]) ++ch;
-    const int64_t base = (tile - tab.tile_prefix[ch]) * TILE;
-    const int64_t n = tab.n[ch];
-    Tile t;
-    t.vals = reinterpret_cast<const VT*>(tab.values[ch]) + base;
-    t.codes = reinterpret_cast<const CT*>(tab.codes[ch]) + base;
-    t.rows = (n - base < TILE) ? (n - base) : TILE;
-    t.full = t.rows == TILE && ((reinterpret_cast<uintptr_t>(t.vals) | reinterpret_cast<uintptr_t>(t.codes)) & 15) == 0;
-    return t;
-  };
-  // One elected thread per CTA additionally asks L2 for the tile kPrefetchTiles ahead with a bulk prefetch
-  // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2): the register prefetch one tile ahead then hits L2 instead
-  // of paying DRAM latency (ncu r01: the first use of a loaded register was still 28% of the stall samples).
-  int pf_ch = 0;
-  auto prefetch_l2 = [&](int64_t t) {
-    if (kPrefetchTiles == 0 || threadIdx.x != 0 || t >= total_tiles) return;
-    while (t >= tab.tile_prefix[pf_ch + 1]) ++pf_ch;
-    const int64_t base = (t - tab.tile_prefix[pf_ch]) * TILE;
-    const int64_t rows = (tab.n[pf_ch] - base < TILE) ? (tab.n[pf_ch] - base) : TILE;
-    const VT* pv = reinterpret_cast<const VT*>(tab.values[pf_ch]) + base;
-    const CT* pc = reinterpret_cast<const CT*>(tab.codes[pf_ch]) + base;
-    const unsigned bv = (unsigned)((rows * sizeof(VT)) & ~(size_t)15), bc = (unsigned)((rows * sizeof(CT)) & ~(size_t)15);
-    if (((reinterpret_cast<uintptr_t>(pv) | reinterpret_cast<uintptr_t>(pc)) & 15) == 0 && bv && bc) {
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pv), "r"(bv) : "memory");
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc), "r"(bc) : "memory");
-    }
-  };
-  // Register pipeline two tiles deep: three statically named buffers rotate through load -> wait -> process.
-  Vec4<VT> vb[3];
-  Vec4<CT> cb[3];
-  Tile tb[3];
-  const int64_t step = gridDim.x;
-  int64_t tile = blockIdx.x;
-  for (int d = 2; d <= kPrefetchTiles; ++d) prefetch_l2(tile + (int64_t)d * step);
-  auto issue = [&](int slot, int64_t t) {
-    tb[slot] = Tile{};
-    if (t < total_tiles) {
-      tb[slot] = locate(t);
-      if (tb[slot].full) {
-        vb[slot] = load4<VT>(tb[slot].vals + threadIdx.x * 4);
-        cb[slot] = load4<CT>(tb[slot].codes + threadIdx.x * 4);
-      }
-    }
-  };
-  auto consume = [&](int slot) {
-    if (tb[slot].full) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) add_row(vb[slot].v[k], cb[slot].v[k]);
-    } else {
-      for (int64_t i = threadIdx.x; i < tb[slot].rows; i += THREADS) add_row(tb[slot].vals[i], tb[slot].codes[i]);
-    }
-    after_tile();
-  };
-  issue(0, tile);
-  issue(1, tile + step);
-  while (tile < total_tiles) {
-    // sub-step A: load slot 2, process slot 0
-    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
-    issue(2, tile + 2 * step);
-    consume(0);
-    tile += step;
-    if (tile >= total_tiles) break;
-    // sub-step B: load slot 0, process slot 1
-    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
-    issue(0, tile + 2 * step);
-    consume(1);
-    tile += step;
-    if (tile >= total_tiles) break;
-    // sub-step C: load slot 1, process slot 2
-    prefetch_l2(tile + (int64_t)(kPrefetchTiles + 1) * step);
-    issue(1, tile + 2 * step);
-    consume(2);
-    tile += step;
-  }
-}
-
-// Lean variant of the persistent walk (tools/kbench3.py: the three-buffer walk above costs 6-11 points of
-// HBM roofline against a bare two-buffer loop).  The hot loop only ever sees FULL, 16-byte-aligned tiles:
+// Persistent walk over the tiles (THREADS*4 rows each) of a chunk table.  (tools/kbench3.py: a three-buffer
+// walk with per-tile chunk lookup and partial-tile branches cost 6-11 points of HBM roofline against this
+// two-buffer loop.)  The hot loop only ever sees FULL, 16-byte-aligned tiles:
 // CTA b takes every gridDim.x-th full tile of the concatenated chunks (the round-robin position carries over
 // chunk boundaries, so the load stays balanced), with the 128-bit loads of its next tile in flight while
 // `add_row(value, code)` runs on the current one.  Chunk tails (n % TILE rows) and unaligned chunks are
 // handled afterwards by a scalar loop, spread over the CTAs.  `after_tile()` runs once per full tile.
 template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
-__device__ __forceinline__ void walk_tiles2(const ChunkTable& tab, AddRow add_row, AfterTile after_tile) {
+__device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row, AfterTile after_tile) {
   constexpr int TILE = THREADS * 4;
   const int nch = tab.nchunks;
   auto full_tiles = [&](int k) -> int64_t {
@@ -311,6 +210,23 @@ __device__ __forceinline__ void walk_tiles2(const ChunkTable& tab, AddRow add_ro
       for (int64_t i = base + threadIdx.x; i < end; i += THREADS) add_row(vals[i], codes[i]);
     }
   }
+}
+
+// Host side: fill `tab` with chunks [c0, c0 + m) and return the number of tiles (of `tile` rows) they hold, or a
+// negative FLOXB_E* code.
+inline int64_t fill_chunk_table(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t c0, int64_t tile, ChunkTable* tab) {
+  const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
+  tab->nchunks = m;
+  int64_t tiles = 0;
+  for (int k = 0; k < m; ++k) {
+    const floxb_chunk_t& ch = chunks[c0 + k];
+    if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+    tab->values[k] = ch.values;
+    tab->codes[k] = ch.codes;
+    tab->n[k] = ch.n;
+    tiles += (ch.n + tile - 1) / tile;
+  }
+  return tiles;
 }
 
 inline int sm_count() {

@@ -17,7 +17,7 @@ template <typename K, bool IS_MAX> __device__ __forceinline__ void key_update(K*
 // lanes of a warp never collide on an address or a bank, which matters for small G.
 template <typename VT, typename CT, bool IS_MAX, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, long long* __restrict__ gkey,
+k_minmax_smem(const __grid_constant__ ChunkTable tab, int G, long long* __restrict__ gkey,
               unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
   using K = typename Key<VT>::type;
   constexpr int TILE = THREADS * 4 * ITERS;
@@ -48,7 +48,7 @@ k_minmax_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G
     }
   };
 
-  walk_tiles2<VT, CT, THREADS>(tab, accum, [] {});
+  walk_tiles<VT, CT, THREADS>(tab, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -131,7 +131,7 @@ int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
   if (force_path == 2) use_smem = false;
   if (use_smem) {
     constexpr int TILE = kMMThreads * 4 * kMMIters;
-    using KernT = void (*)(const ChunkTable, int64_t, int, long long*, unsigned long long*, unsigned long long*);
+    using KernT = void (*)(const ChunkTable, int, long long*, unsigned long long*, unsigned long long*);
     KernT kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 0>;
     size_t smem_used = smem;
     if (smem * 32 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 5>; smem_used = smem * 32; }
@@ -140,22 +140,12 @@ int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
       return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
       ChunkTable tab;
-      const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
-      tab.nchunks = m;
-      tab.tile_prefix[0] = 0;
-      for (int k = 0; k < m; ++k) {
-        const floxb_chunk_t& ch = chunks[c0 + k];
-        if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
-        tab.values[k] = ch.values;
-        tab.codes[k] = ch.codes;
-        tab.n[k] = ch.n;
-        tab.tile_prefix[k + 1] = tab.tile_prefix[k] + (ch.n + TILE - 1) / TILE;
-      }
-      const int64_t tiles = tab.tile_prefix[m];
+      const int64_t tiles = fill_chunk_table(chunks, n_chunks, c0, TILE, &tab);
+      if (tiles < 0) return (int)tiles;
       if (tiles == 0) continue;
       if (tiles / sm_count() * TILE >= (int64_t)1 << 32) return FLOXB_ERANGE;
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-      kern<<<grid, kMMThreads, smem_used, st>>>(tab, tiles, (int)G, gkey, gcnt, gnan);
+      kern<<<grid, kMMThreads, smem_used, st>>>(tab, (int)G, gkey, gcnt, gnan);
     }
   } else {
     for (int64_t k = 0; k < n_chunks; ++k) {

@@ -54,7 +54,7 @@ template <typename VT, int OP> struct Slot {
 // G = 1e4).  The launcher picks the largest replication that fits shared memory.
 template <typename VT, typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G,
+k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
                typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
                unsigned long long* __restrict__ gnan) {
   using AccT = typename Acc<VT>::type;
@@ -99,7 +99,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int 
     }
   };
 
-  walk_tiles2<VT, CT, THREADS>(tab, accum, [] {});
+  walk_tiles<VT, CT, THREADS>(tab, accum, [] {});
   __syncthreads();
 
   for (int g = threadIdx.x; g < G; g += THREADS) {
@@ -154,7 +154,7 @@ constexpr unsigned kDrainEvery = 32;  // <= this many (+ racing) addends per f32
 // (tools/kbench.py: the same loop runs 26% slower with 200 KB than with 120 KB of dynamic shared memory).
 template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT, bool WS>
 __global__ void __launch_bounds__(THREADS, 1)
-k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, double* __restrict__ gacc,
+k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int G, double* __restrict__ gacc,
                    unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan,
                    double* __restrict__ workspace) {
   constexpr int TILE = THREADS * 4 * ITERS;
@@ -206,7 +206,7 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int64_t total_tiles, 
   // (moved by the next sweep); its count may travel one sweep later than its value, which only matters to the
   // drain heuristic.  (tools/kbench3.py: __syncthreads-fenced sweeps cost 7 points of roofline, these 2.)
   int since_sweep = 0;
-  walk_tiles2<float, CT, THREADS>(tab, add_row, [&] {
+  walk_tiles<float, CT, THREADS>(tab, add_row, [&] {
     if (++since_sweep == kSweepTiles) {
       since_sweep = 0;
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
@@ -396,8 +396,8 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   if (use_smem) {
     constexpr int kIters = kSmemIters;
     constexpr int TILE = kSmemThreads * 4 * kIters;
-    using KernT = void (*)(const ChunkTable, int64_t, int, AccT*, unsigned long long*, unsigned long long*);
-    using KernWsT = void (*)(const ChunkTable, int64_t, int, double*, unsigned long long*, unsigned long long*, double*);
+    using KernT = void (*)(const ChunkTable, int, AccT*, unsigned long long*, unsigned long long*);
+    using KernWsT = void (*)(const ChunkTable, int, double*, unsigned long long*, unsigned long long*, double*);
     KernT kern = nullptr;
     KernWsT kern_ws = nullptr;
     size_t smem_used = smem;
@@ -417,27 +417,17 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
       return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
       ChunkTable tab;
-      const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
-      tab.nchunks = m;
-      tab.tile_prefix[0] = 0;
-      for (int k = 0; k < m; ++k) {
-        const floxb_chunk_t& ch = chunks[c0 + k];
-        if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
-        tab.values[k] = ch.values;
-        tab.codes[k] = ch.codes;
-        tab.n[k] = ch.n;
-        tab.tile_prefix[k + 1] = tab.tile_prefix[k] + (ch.n + TILE - 1) / TILE;
-      }
-      const int64_t tiles = tab.tile_prefix[m];
+      const int64_t tiles = fill_chunk_table(chunks, n_chunks, c0, TILE, &tab);
+      if (tiles < 0) return (int)tiles;
       if (tiles == 0) continue;
       // u32 per-CTA counters: keep rows per CTA below 2^32
       if (tiles / sm_count() * TILE >= (int64_t)1 << 32) return FLOXB_ERANGE;
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
       if (kern_ws) {
         if constexpr (kTwoLevel)
-          kern_ws<<<grid, kSmemThreads, smem_used, st>>>(tab, tiles, (int)G, gacc, gcnt, gnan, reinterpret_cast<double*>(workspace));
+          kern_ws<<<grid, kSmemThreads, smem_used, st>>>(tab, (int)G, gacc, gcnt, gnan, reinterpret_cast<double*>(workspace));
       } else {
-        kern<<<grid, kSmemThreads, smem_used, st>>>(tab, tiles, (int)G, gacc, gcnt, gnan);
+        kern<<<grid, kSmemThreads, smem_used, st>>>(tab, (int)G, gacc, gcnt, gnan);
       }
     }
   } else {
@@ -514,6 +504,8 @@ extern "C" int64_t floxb_moments_workspace_bytes(int value_dtype, int64_t A, int
   if ((size_t)n_groups * 8 + (size_t)((n_groups + 31) / 32) * 4 > kSmemBudget) return 0;  // L2-atomic path
   return (int64_t)sm_count() * (n_groups * 12 + 8);
 }
+
+extern "C" int floxb_max_chunks_per_launch(void) { return floxb::kMaxChunksPerLaunch; }
 
 extern "C" int64_t floxb_smem_group_limit(int value_dtype, int family) {
   // family 0: f32 sums use the two-level kernel (20 B / group), everything else one 64-bit slot

@@ -32,7 +32,7 @@ __global__ void k_group_means(const typename Acc<VT>::type* __restrict__ acc, co
 // ---- squared deviations -----------------------------------------------------------------
 template <typename VT, typename CT, int THREADS, int ITERS>
 __global__ void __launch_bounds__(THREADS, 1)
-k_sqdev_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G, const double* __restrict__ means,
+k_sqdev_smem(const __grid_constant__ ChunkTable tab, int G, const double* __restrict__ means,
              int skipna, double* __restrict__ gm2) {
   constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,7 +65,7 @@ k_sqdev_smem(const __grid_constant__ ChunkTable tab, int64_t total_tiles, int G,
       }
     }
   };
-  walk_tiles2<VT, CT, THREADS>(tab, accum, [] {});
+  walk_tiles<VT, CT, THREADS>(tab, accum, [] {});
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += THREADS) {
     const double s = (double)sm2[g];
@@ -160,21 +160,11 @@ int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
       ChunkTable tab;
-      const int m = (int)((n_chunks - c0 < kMaxChunksPerLaunch) ? (n_chunks - c0) : kMaxChunksPerLaunch);
-      tab.nchunks = m;
-      tab.tile_prefix[0] = 0;
-      for (int k = 0; k < m; ++k) {
-        const floxb_chunk_t& ch = chunks[c0 + k];
-        if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
-        tab.values[k] = ch.values;
-        tab.codes[k] = ch.codes;
-        tab.n[k] = ch.n;
-        tab.tile_prefix[k + 1] = tab.tile_prefix[k] + (ch.n + TILE - 1) / TILE;
-      }
-      const int64_t tiles = tab.tile_prefix[m];
+      const int64_t tiles = fill_chunk_table(chunks, n_chunks, c0, TILE, &tab);
+      if (tiles < 0) return (int)tiles;
       if (tiles == 0) continue;
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-      kern<<<grid, kSqThreads, smem, st>>>(tab, tiles, (int)G, means, skipna, m2);
+      kern<<<grid, kSqThreads, smem, st>>>(tab, (int)G, means, skipna, m2);
     }
   } else {
     for (int64_t k = 0; k < n_chunks; ++k) {

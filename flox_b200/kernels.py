@@ -45,7 +45,7 @@ class CudaKernels:
         # FLOXB_WORKSPACE=0 keeps the f64 level of the f32 shared-memory kernel in shared memory (profiling knob)
         self.use_workspace = os.environ.get("FLOXB_WORKSPACE", "1") != "0"
         # CUDA kernel launches issued by the library (mirrors the launch logic of csrc/*.cu:
-        # optional fill kernel + one launch per <=48-chunk table on the shared-memory path, or one
+        # optional fill kernel + one launch per chunk table (<= floxb_max_chunks_per_launch) on the shared-memory path, or one
         # per non-empty chunk on the L2-atomic path).  bench.py reports it as `gpu_launches`.
         self.kernel_launches = 0
         self._limits: dict = {}
@@ -60,8 +60,9 @@ class CudaKernels:
                 self._limits[key] = self.smem_group_limit(vdt, family)
             smem = has_smem_path and A == 1 and B == 1 and G <= self._limits[key] and force_path != 2
             if smem:
-                for lo in range(0, len(chunks), 48):
-                    if any(c.numel() > 0 for _, c in chunks[lo:lo + 48]):
+                per = self.max_chunks_per_launch()
+                for lo in range(0, len(chunks), per):
+                    if any(c.numel() > 0 for _, c in chunks[lo:lo + per]):
                         n += 1
             else:
                 n += nonempty
@@ -241,6 +242,9 @@ class CudaKernels:
 
     def smem_group_limit(self, value_dtype, family: int) -> int:
         return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))
+
+    def max_chunks_per_launch(self) -> int:
+        return int(L.load().floxb_max_chunks_per_launch())
 
 
 _backend = None

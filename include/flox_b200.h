@@ -78,6 +78,9 @@ const char* floxb_last_cuda_error(void);
 /* Largest n_groups the shared-memory (privatised-bin) kernel path takes for this op family;
  * above it the L2-atomic path is used.  Informational. */
 int64_t floxb_smem_group_limit(int value_dtype, int family /*0 moments, 1 minmax*/);
+/* How many chunks (dask blocks, flox/core.py:1614-1626 `map_blocks(chunk_reduce)`) one persistent launch of the
+ * shared-memory path walks; longer chunk lists are split into several launches.  Informational. */
+int floxb_max_chunks_per_launch(void);
 
 /* Grouped sum / product / sum-of-squares plus non-NaN and NaN counts, one pass.
  * Replaces aggregate_flox._np_grouped_op(op=np.add|multiply.reduceat) and nanlen

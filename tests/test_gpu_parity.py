@@ -127,6 +127,38 @@ def test_seeded_vs_oracle(N, ngroups, dtype):
         assert_same(got, want, what=f"{func}/{np.dtype(dtype)}/{N}/{ngroups}", **_tols(func, x))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+def test_ragged_unaligned_chunk_tables(dtype):
+    """The persistent chunk-table walk (csrc/common.cuh:walk_tiles): 300 ragged chunks (more than one
+    table of floxb_max_chunks_per_launch), empty chunks, chunks shorter than a tile, chunks that are
+    views starting 1..3 elements into an allocation (not 16-byte aligned: scalar path), chunk tails."""
+    rng = np.random.default_rng(77)
+    ngroups = 1000
+    sizes = [0, 1, 3, 4095, 4096, 4097, 8192 + 5, 50_000, 0, 123_457] + list(rng.integers(1, 30_000, 290))
+    N = int(sum(sizes))
+    if np.dtype(dtype).kind == "f":
+        x = (rng.random(N) * 4 - 1).astype(dtype)
+        x[rng.random(N) < 0.01] = np.nan
+    else:
+        x = rng.integers(-1000, 1000, N).astype(dtype)
+    by = rng.integers(-1, ngroups, N)
+    # device copies with a 1..3-element lead so that chunk k starts (off_k + lead) elements into the buffer
+    for lead in (0, 1, 3):
+        xd = torch.empty(N + lead, dtype=torch.as_tensor(x[:1]).dtype, device="cuda")
+        bd = torch.empty(N + lead, dtype=torch.int64, device="cuda")
+        xd[lead:] = torch.as_tensor(x)
+        bd[lead:] = torch.as_tensor(by)
+        offs = np.concatenate([[0], np.cumsum(sizes)]) + lead
+        xs = [xd[offs[i]:offs[i + 1]] for i in range(len(sizes))]
+        bs = [bd[offs[i]:offs[i + 1]] for i in range(len(sizes))]
+        arr, lab = ChunkedArray(xs), ChunkedArray(bs)
+        for func in ("sum", "nanmean", "nanmax", "min", "count", "nanvar"):
+            got, _ = flox_b200.groupby_reduce(arr, lab, func=func, expected_groups=np.arange(ngroups), method="map-reduce")
+            want, _ = O.groupby_reduce(x, by, func=func, expected_groups=np.arange(ngroups))
+            got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+            assert_same(got, want, what=f"ragged/{func}/{np.dtype(dtype)}/lead{lead}", **_tols(func, x))
+
+
 @pytest.mark.parametrize("func", ["argmax", "argmin", "nanargmax", "nanargmin"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
 def test_arg_reductions(func, dtype):

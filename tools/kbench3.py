@@ -39,7 +39,7 @@ def main():
     acc = torch.zeros(G, dtype=torch.float64, device="cuda")
     cnt = torch.zeros(G, dtype=torch.int64, device="cuda")
     ws = torch.empty(sms * (G * 12 + 64) // 8 + 8, dtype=torch.float64, device="cuda")
-    variants = [int(v) for v in os.environ.get("KBENCH_VARIANTS", ",".join(map(str, range(20)))).split(",")]
+    variants = [int(v) for v in os.environ.get("KBENCH_VARIANTS", "0,6,8,10,11,12,13,14,15,16,17,18,19").split(",")]
     st = torch.cuda.current_stream().cuda_stream
     out = []
     for rnd in range(2):  # two rounds: order effects / clock drift show up as disagreement

@@ -1,6 +1,7 @@
 // Bisect harness: which feature of the production two-level kernel (flox_b200/csrc/moments.cu) costs what,
 // relative to the bare software-pipelined loop of tools/kexp.cu variant 22.  Uses the production walk_tiles.
-// Built and timed by tools/kbench3.py on the GPU box.
+// Built and timed by tools/kbench3.py on the GPU box.  Variants 1-5, 7, 9 measured the earlier three-buffer
+// walk (removed; numbers kept in profiles/r01_kbench3_bisect_oldwalk.json).
 #include "../flox_b200/csrc/common.cuh"
 
 using namespace floxb;
@@ -11,7 +12,7 @@ enum : unsigned { F_WALK = 1, F_NAN = 2, F_RET = 4, F_SWEEP = 8, F_WS = 16, F_NO
 
 template <unsigned F>
 __global__ void __launch_bounds__(1024, 1)
-k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const float* __restrict__ vals,
+k_bisect(const __grid_constant__ ChunkTable tab, const float* __restrict__ vals,
          const long long* __restrict__ codes, int64_t n, int G, double* __restrict__ gacc,
          unsigned long long* __restrict__ gcnt, double* __restrict__ workspace) {
   constexpr int THREADS = 1024;
@@ -98,10 +99,7 @@ k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const floa
   };
 
   if constexpr ((F & F_WALK2) != 0) {
-    walk_tiles2<float, int64_t, THREADS>(tab, add_row, after_tile);
-  } else if constexpr ((F & F_WALK) != 0) {
-    constexpr int PF = (F & F_NOPF) ? 0 : ((F & F_PF8) ? 8 : 4);
-    walk_tiles<float, int64_t, THREADS, PF>(tab, total_tiles, add_row, after_tile);
+    walk_tiles<float, int64_t, THREADS>(tab, add_row, after_tile);
   } else {
     // bare depth-1 register pipeline over one flat array (kexp.cu variant 22)
     const int64_t tiles = n / TILE;
@@ -139,13 +137,13 @@ k_bisect(const __grid_constant__ ChunkTable tab, int64_t total_tiles, const floa
 }
 
 template <unsigned F>
-int launch(const ChunkTable& tab, int64_t total_tiles, const float* v, const long long* c, int64_t n, int G, double* acc,
+int launch(const ChunkTable& tab, const float* v, const long long* c, int64_t n, int G, double* acc,
            unsigned long long* cnt, double* ws, int grid, cudaStream_t st) {
   const bool l2_in_smem = (F & F_SWEEP) && !(F & F_WS);
   const size_t smem = (size_t)G * (l2_in_smem ? 20 : 8) + ((G + 31) / 32) * 4 + 16;
   auto k = k_bisect<F>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  k<<<grid, 1024, smem, st>>>(tab, total_tiles, v, c, n, G, acc, cnt, ws);
+  k<<<grid, 1024, smem, st>>>(tab, v, c, n, G, acc, cnt, ws);
   return (int)cudaGetLastError();
 }
 
@@ -157,28 +155,17 @@ extern "C" int kexp3_run(int variant, const float* v, const long long* c, int64_
   ChunkTable tab{};
   const int64_t per = n / nchunks;
   tab.nchunks = nchunks;
-  tab.tile_prefix[0] = 0;
   for (int i = 0; i < nchunks; ++i) {
     tab.values[i] = v + (int64_t)i * per;
     tab.codes[i] = c + (int64_t)i * per;
     tab.n[i] = per;
-    tab.tile_prefix[i + 1] = tab.tile_prefix[i] + (per + 4095) / 4096;
   }
-  for (int i = nchunks; i < kMaxChunksPerLaunch; ++i) tab.tile_prefix[i + 1] = tab.tile_prefix[nchunks];
-  const int64_t tt = tab.tile_prefix[nchunks];
   cudaStream_t st = (cudaStream_t)stream;
-#define V(ID, FLAGS) case ID: return launch<(FLAGS)>(tab, tt, v, c, n, G, acc, cnt, ws, grid, st);
+#define V(ID, FLAGS) case ID: return launch<(FLAGS)>(tab, v, c, n, G, acc, cnt, ws, grid, st);
   switch (variant) {
     V(0, 0u)
-    V(1, F_WALK)
-    V(2, F_WALK | F_NAN)
-    V(3, F_WALK | F_NAN | F_RET)
-    V(4, F_WALK | F_NAN | F_RET | F_SWEEP)
-    V(5, F_WALK | F_NAN | F_RET | F_SWEEP | F_WS)
     V(6, F_NAN | F_RET | F_SWEEP | F_WS)
-    V(7, F_WALK | F_NOPF)
     V(8, F_NAN | F_RET)
-    V(9, F_WALK | F_PF8)
     V(10, F_SWEEP | F_WS)
     V(11, F_NAN)
     V(12, F_RET)
