@@ -18,6 +18,15 @@ _TORCH2NP[torch.bfloat16] = np.dtype("float32")
 _KERNEL_DTYPES = (torch.float32, torch.float64, torch.int32, torch.int64)
 
 
+class TransferStats:
+    """Bytes moved host -> device by this package (bench.py reports them as h2d_bytes_per_step)."""
+    h2d_bytes = 0
+
+
+def count_h2d(t: torch.Tensor) -> None:
+    TransferStats.h2d_bytes += t.numel() * t.element_size()
+
+
 def is_torch(x) -> bool:
     return isinstance(x, torch.Tensor)
 
@@ -64,6 +73,8 @@ def to_device(x, device: torch.device | None = None, *, dtype: torch.dtype | Non
         elif a.dtype.kind == "u" and a.dtype.itemsize > 1:
             a = a.astype(np.int64)
         t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.device != device and device.type == "cuda" and t.device.type == "cpu":
+        count_h2d(t)
     if dtype is not None and t.dtype != dtype:
         t = t.to(device=device, dtype=dtype, non_blocking=True)
     elif t.device != device:

@@ -1,0 +1,68 @@
+// flox_b200 — label staging for host-resident chunks (include/flox_b200.h: floxb_host_pack_codes,
+// floxb_widen_codes).  flox hands every block int64 codes (flox/factorize.py:201-210); for an f32 reduction they are
+// 8 of the 12 bytes per row that cross PCIe.  With fewer than 2^15 groups the host narrows them to int16 on the
+// way into the pinned staging buffer (one pass, parallelised over chunks by the caller) and the device widens them
+// to the int32 the reduction kernels read: 6 instead of 12 bytes per row over the link.
+#include "common.cuh"
+
+namespace floxb {
+
+template <typename IT, typename OT>
+static void pack_codes(const IT* __restrict__ in, int64_t n, int64_t n_groups, OT* __restrict__ out) {
+  const uint64_t g = (uint64_t)n_groups;
+  for (int64_t i = 0; i < n; ++i) {
+    const IT c = in[i];
+    out[i] = ((uint64_t)(int64_t)c < g) ? (OT)c : (OT)-1;  // negative codes wrap to huge unsigned values
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_widen_codes(const short4* __restrict__ in4, const int16_t* __restrict__ in, int64_t n, int4* __restrict__ out4,
+              int32_t* __restrict__ out) {
+  const int64_t nvec = in4 ? n / 4 : 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec; q += stride) {
+    const short4 s = in4[q];
+    out4[q] = make_int4(s.x, s.y, s.z, s.w);
+  }
+  for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+}
+
+}  // namespace floxb
+
+using namespace floxb;
+
+extern "C" int floxb_host_pack_codes(const void* codes, int code_dtype, int64_t n, int64_t n_groups, void* out, int out_bits) {
+  if (n < 0 || n_groups < 0) return FLOXB_EINVAL;
+  if (n == 0) return FLOXB_OK;
+  if (!codes || !out) return FLOXB_EINVAL;
+  if (out_bits == 16) {
+    if (n_groups > 32767) return FLOXB_ERANGE;
+    if (code_dtype == FLOXB_I64) pack_codes(static_cast<const int64_t*>(codes), n, n_groups, static_cast<int16_t*>(out));
+    else if (code_dtype == FLOXB_I32) pack_codes(static_cast<const int32_t*>(codes), n, n_groups, static_cast<int16_t*>(out));
+    else return FLOXB_EDTYPE;
+  } else if (out_bits == 32) {
+    if (n_groups > 2147483647LL) return FLOXB_ERANGE;
+    if (code_dtype == FLOXB_I64) pack_codes(static_cast<const int64_t*>(codes), n, n_groups, static_cast<int32_t*>(out));
+    else if (code_dtype == FLOXB_I32) pack_codes(static_cast<const int32_t*>(codes), n, n_groups, static_cast<int32_t*>(out));
+    else return FLOXB_EDTYPE;
+  } else {
+    return FLOXB_EINVAL;
+  }
+  return FLOXB_OK;
+}
+
+extern "C" int floxb_widen_codes(const int16_t* codes16, int64_t n, int32_t* codes32, void* stream) {
+  if (n < 0) return FLOXB_EINVAL;
+  if (n == 0) return FLOXB_OK;
+  if (!codes16 || !codes32) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = (reinterpret_cast<uintptr_t>(codes16) & 7) == 0 && (reinterpret_cast<uintptr_t>(codes32) & 15) == 0;
+  int64_t blocks = (n / 4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  k_widen_codes<<<(unsigned)blocks, 256, 0, st>>>(vec ? reinterpret_cast<const short4*>(codes16) : nullptr, codes16, n,
+                                                 reinterpret_cast<int4*>(codes32), codes32);
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}

@@ -246,6 +246,22 @@ class CudaKernels:
     def max_chunks_per_launch(self) -> int:
         return int(L.load().floxb_max_chunks_per_launch())
 
+    # -- label staging (csrc/staging.cu) ------------------------------------------------------
+    @staticmethod
+    def host_pack_codes(codes_np, n_groups: int, out: torch.Tensor) -> None:
+        """HOST function (no CUDA call; releases the GIL): range-check + narrow int32/int64 codes into `out`
+        (a pinned int16 / int32 tensor).  Called from worker threads, one chunk each."""
+        bits = 16 if out.dtype == torch.int16 else 32
+        L.check(L.load().floxb_host_pack_codes(codes_np.ctypes.data, L.I64 if codes_np.dtype.itemsize == 8 else L.I32, codes_np.size, int(n_groups),
+                                               out.data_ptr(), bits), "floxb_host_pack_codes")
+
+    def widen_codes(self, codes16: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(codes16.shape, dtype=torch.int32, device=codes16.device)
+        L.check(L.load().floxb_widen_codes(codes16.data_ptr(), codes16.numel(), out.data_ptr(), self._stream()), "floxb_widen_codes")
+        self.launches += 1
+        self.kernel_launches += 1 if codes16.numel() else 0
+        return out
+
 
 _backend = None
 

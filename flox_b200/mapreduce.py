@@ -20,6 +20,8 @@ intermediates (API parity and the golden tests).
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pandas as pd
@@ -28,10 +30,10 @@ import torch
 from . import parallel
 from .accumulate import GroupedAccumulators
 from .aggregations import Aggregation, _is_arg_reduction, is_var_chunk_reduction, var_chunk
-from .arrays import from_device, is_torch, kernel_dtype, to_device
+from .arrays import count_h2d, from_device, is_torch, kernel_dtype, to_device
 from .chunked import ChunkedArray, is_chunked
 from .core import DUMMY_AXIS, _finalize_results
-from .kernels import default_device
+from .kernels import default_device, get_kernels
 from .multiarray import MultiArray
 from .reductions import evaluate, var_triple
 from .reindex import ReindexStrategy
@@ -85,7 +87,59 @@ _CODE_DTYPES = (torch.int32, torch.int64)
 _VALUE_DTYPES = (torch.float32, torch.float64, torch.int32, torch.int64)
 
 
-def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext, need_global_index: bool = False):
+_pack_pool: ThreadPoolExecutor | None = None
+
+
+def _pool(world: int) -> ThreadPoolExecutor:
+    global _pack_pool
+    if _pack_pool is None:
+        _pack_pool = ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 1) // max(world, 1))),
+                                        thread_name_prefix="floxb-pack")
+    return _pack_pool
+
+
+def _host_codes(c):
+    """A C-contiguous 1-D int32/int64 numpy view of a HOST label chunk, else None."""
+    if is_torch(c):
+        if c.device.type != "cpu" or c.dtype not in _CODE_DTYPES or not c.is_contiguous():
+            return None
+        c = c.numpy()
+    elif not isinstance(c, np.ndarray):
+        return None
+    if c.dtype not in (np.dtype("int32"), np.dtype("int64")) or c.ndim != 1 or not c.flags.c_contiguous:
+        return None
+    return c
+
+
+def _stage_packed_codes(label_chunks: dict, n_groups: int, device, world: int) -> dict:
+    """Host-resident integer label chunks -> device int32 codes, moving 2 (4) instead of 8 bytes per row over
+    PCIe when the groups fit 16 (32) bits: worker threads range-check + narrow each chunk into a pinned staging
+    buffer (floxb_host_pack_codes), the copies are enqueued as the packs finish, int16 is widened on the device
+    (floxb_widen_codes).  Returns {chunk index: device codes}; chunks it does not take are left to the caller."""
+    if device.type != "cuda" or n_groups > 2**31 - 1:
+        return {}
+    todo = {}
+    for k, c in label_chunks.items():
+        h = _host_codes(c)
+        if h is not None and h.size and (n_groups <= 32767 or h.dtype == np.dtype("int64")):
+            todo[k] = h
+    if not todo:
+        return {}
+    sdt = torch.int16 if n_groups <= 32767 else torch.int32
+    kern, pool = get_kernels(), _pool(world)
+    staged = {k: torch.empty(h.size, dtype=sdt, pin_memory=True) for k, h in todo.items()}
+    futures = {k: pool.submit(kern.host_pack_codes, h, n_groups, staged[k]) for k, h in todo.items()}
+    out = {}
+    for k in todo:
+        futures[k].result()
+        count_h2d(staged[k])
+        d = staged[k].to(device, non_blocking=True)
+        out[k] = kern.widen_codes(d) if sdt == torch.int16 else d
+    return out
+
+
+def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext, need_global_index: bool = False,
+                         n_groups: int | None = None):
     """Device tensors `(values[A, n_k, 1], codes[n_k])` for the chunks this rank owns, plus the
     global position of each chunk's first element along the reduced axis (only arg-reductions need
     positions that are global across ranks: that costs one small all-gather of shard lengths)."""
@@ -103,17 +157,19 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     first = array.chunks[0]
     kdt = kernel_dtype(first.dtype if is_torch(first) else to_device(first[..., :0], device).dtype)
     chunks, index_base = [], []
-    for k in mine:
+    labels = {k: (by_chunks[k] if by_chunks is not None else by[..., int(offsets[k]):int(offsets[k]) + sizes[k]]) for k in mine}
+    values = {}
+    for k in mine:  # all value copies are enqueued first: the link is busy while the worker threads pack labels
         v = array.chunks[k]
         if not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
             v = to_device(v, device)
             if v.dtype != kdt:
                 v = v.to(kdt)
-        if by_chunks is not None:
-            c = by_chunks[k]
-        else:
-            lo = int(offsets[k])
-            c = by[..., lo:lo + sizes[k]]
+        values[k] = v
+    packed = _stage_packed_codes(labels, n_groups, device, ctx.comm.world_size if ctx.comm.enabled else 1) if n_groups else {}
+    for k in mine:
+        v = values[k]
+        c = packed.get(k, labels[k])
         if not (is_torch(c) and c.device == device and c.dtype in _CODE_DTYPES and c.is_contiguous()):
             c = to_device(c, device)
             if c.dtype not in _CODE_DTYPES:
@@ -131,7 +187,8 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
         raise NotImplementedError("chunked inputs are grouped by 1-D labels along the chunked (last) axis")
     ctx = parallel.current()
     G = len(expected_groups)
-    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg))
+    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg),
+                                                                    n_groups=G)
     acc = GroupedAccumulators(chunks, A, 1, G, kdt, device, index_base=index_base, comm=ctx.comm)
     like = array.chunks[0]
     array_np_dtype = array.dtype

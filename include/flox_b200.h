@@ -186,6 +186,16 @@ int floxb_digitize(const void* labels, int label_dtype, int64_t n, const double*
 int floxb_ravel_codes(const int64_t* c0, const int64_t* c1, int64_t n, int64_t size0, int64_t size1,
                       int64_t* out, void* stream);
 
+/* Label staging for host-resident chunks.  flox hands every block int64 codes (flox/factorize.py:201-210,
+ * flox/core.py:298-316); over PCIe they are 2/3 of the bytes of an f32 reduction.  When n_groups < 2^15 (2^31) the
+ * codes fit 16 (32) bits:
+ *   floxb_host_pack_codes  (HOST function, no CUDA call; thread-safe, callers parallelise over chunks):
+ *       out[i] = codes[i] if 0 <= codes[i] < n_groups else -1, narrowed to int16 / int32.  `out` is normally a
+ *       pinned staging buffer.  code_dtype FLOXB_I32 / FLOXB_I64, out_bits 16 or 32.
+ *   floxb_widen_codes      (device): int16 codes -> int32 codes, the narrowest type the reduction kernels read. */
+int floxb_host_pack_codes(const void* codes, int code_dtype, int64_t n, int64_t n_groups, void* out, int out_bits);
+int floxb_widen_codes(const int16_t* codes16, int64_t n, int32_t* codes32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,3 +298,13 @@ class EmuKernels:
 
     def smem_group_limit(self, value_dtype, family):
         return 14000
+
+    def max_chunks_per_launch(self):
+        return 128
+
+    @staticmethod
+    def host_pack_codes(codes_np, n_groups, out):
+        _np(out)[...] = np.where((codes_np >= 0) & (codes_np < n_groups), codes_np, -1)
+
+    def widen_codes(self, codes16):
+        return codes16.to(torch.int32)

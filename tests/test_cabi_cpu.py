@@ -44,6 +44,27 @@ def test_argument_validation_without_gpu():
     assert lib.floxb_smem_group_limit(_lib.F32, 0) >= 10_000
 
 
+@pytest.mark.parametrize("src", ["int64", "int32"])
+@pytest.mark.parametrize("bits", [16, 32])
+def test_host_pack_codes(src, bits):
+    """floxb_host_pack_codes is a HOST function (label staging, include/flox_b200.h): out-of-range and negative
+    codes become -1 — exactly the rows the reduction kernels skip — everything else is narrowed unchanged."""
+    import numpy as np
+
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    G = 30_000
+    c = rng.integers(-50, G + 50, 100_003).astype(src)
+    c[:6] = [0, G - 1, G, -1, np.iinfo(src).max, np.iinfo(src).min]
+    out = np.full(c.size, 7, dtype=f"int{bits}")
+    rc = lib.floxb_host_pack_codes(c.ctypes.data, _lib.I64 if src == "int64" else _lib.I32, c.size, G, out.ctypes.data, bits)
+    assert rc == 0
+    want = np.where((c >= 0) & (c < G), c, -1).astype(out.dtype)
+    np.testing.assert_array_equal(out, want)
+    assert lib.floxb_host_pack_codes(c.ctypes.data, _lib.I64, c.size, 40_000, out.ctypes.data, 16) == -4 or bits == 32
+    assert lib.floxb_host_pack_codes(c.ctypes.data, _lib.F32, c.size, G, out.ctypes.data, bits) == -2
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine WITHOUT a GPU")
 def test_no_cpu_fallback():
     import numpy as np

@@ -159,6 +159,41 @@ def test_ragged_unaligned_chunk_tables(dtype):
             assert_same(got, want, what=f"ragged/{func}/{np.dtype(dtype)}/lead{lead}", **_tols(func, x))
 
 
+@pytest.mark.parametrize("ngroups,label_dtype", [(1000, np.int64), (32767, np.int32), (40_000, np.int64), (40_000, np.int32)])
+def test_host_label_staging(ngroups, label_dtype):
+    """Host-resident chunks: labels are range-checked + narrowed on the host (floxb_host_pack_codes), copied and
+    widened on the device (floxb_widen_codes).  Codes outside [0, G) — including ones that would alias a valid
+    group after a blind int16/int32 cast — must be ignored exactly as on the device-resident path."""
+    from flox_b200.arrays import TransferStats
+
+    rng = np.random.default_rng(31)
+    N = 1_200_007
+    x = (rng.random(N) * 4 - 1).astype(np.float32)
+    by = rng.integers(0, ngroups, N).astype(label_dtype)
+    by[::97] = -1
+    by[5::1013] = ngroups                      # just out of range
+    if label_dtype == np.int64:
+        by[7::2029] = 65536 + 3                # aliases group 3 under a blind int16 cast
+        by[11::4051] = 2**32 + 5               # aliases group 5 under a blind int32 cast
+    want_sum, _ = O.groupby_reduce(x, np.where((by >= 0) & (by < ngroups), by, -1), func="nansum", expected_groups=np.arange(ngroups))
+    for container in ("numpy", "pinned"):
+        if container == "numpy":
+            arr, lab = ChunkedArray.from_array(x, 100_000), ChunkedArray.from_array(by, 100_000)
+        else:
+            arr = ChunkedArray.from_array(torch.from_numpy(x).pin_memory(), 100_000)
+            lab = ChunkedArray.from_array(torch.from_numpy(by).pin_memory(), 100_000)
+        h0 = TransferStats.h2d_bytes
+        got, _ = flox_b200.groupby_reduce(arr, lab, func="nansum", expected_groups=np.arange(ngroups), method="map-reduce")
+        moved = TransferStats.h2d_bytes - h0
+        got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+        assert_same(got, want_sum, what=f"staging/{container}/{ngroups}", **_tols("nansum", x))
+        cnt, _ = flox_b200.groupby_reduce(arr, lab, func="count", expected_groups=np.arange(ngroups), method="map-reduce")
+        cnt = cnt.cpu().numpy() if isinstance(cnt, torch.Tensor) else cnt
+        np.testing.assert_array_equal(cnt, np.bincount(by[(by >= 0) & (by < ngroups)], minlength=ngroups))
+        packed = 2 if ngroups <= 32767 else (4 if label_dtype == np.int64 else np.dtype(label_dtype).itemsize)
+        assert moved == N * (4 + packed), (moved, N, packed)
+
+
 @pytest.mark.parametrize("func", ["argmax", "argmin", "nanargmax", "nanargmin"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
 def test_arg_reductions(func, dtype):
