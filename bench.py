@@ -378,6 +378,16 @@ def run_gpu(args):
         from flox_b200.arrays import TransferStats
 
         e2e_step()
+        if args.profile_host and rank == 0:
+            import cProfile
+            import pstats
+
+            prof = cProfile.Profile()
+            prof.enable()
+            e2e_step()
+            prof.disable()
+            print("---- e2e step host profile ----", file=sys.stderr)
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(18)
         barrier()
         h2d0 = TransferStats.h2d_bytes
         t0 = time.perf_counter()

@@ -5,15 +5,45 @@
 // to the int32 the reduction kernels read: 6 instead of 12 bytes per row over the link.
 #include "common.cuh"
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#define FLOXB_HAVE_SSE2 1
+#endif
+
 namespace floxb {
 
+// The staging buffer is written once and next read by the DMA engine: streaming (non-temporal) 16-byte stores
+// keep it out of the cache and skip the read-for-ownership of every output line (the pack is bound by host
+// memory bandwidth: tools/e2e_probe.py).
 template <typename IT, typename OT>
-static void pack_codes(const IT* __restrict__ in, int64_t n, int64_t n_groups, OT* __restrict__ out) {
-  const uint64_t g = (uint64_t)n_groups;
+static void pack_block(const IT* __restrict__ in, int64_t n, uint64_t g, OT* __restrict__ out) {
   for (int64_t i = 0; i < n; ++i) {
     const IT c = in[i];
     out[i] = ((uint64_t)(int64_t)c < g) ? (OT)c : (OT)-1;  // negative codes wrap to huge unsigned values
   }
+}
+
+template <typename IT, typename OT>
+static void pack_codes(const IT* __restrict__ in, int64_t n, int64_t n_groups, OT* __restrict__ out) {
+  const uint64_t g = (uint64_t)n_groups;
+  int64_t i = 0;
+#ifdef FLOXB_HAVE_SSE2
+  // blocks of 4096 codes are packed into an L1-resident buffer (auto-vectorised loop) and streamed out
+  constexpr int64_t BLK = 4096, V = 16 / sizeof(OT);
+  const int64_t head = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15) / sizeof(OT));
+  if (head <= n && (reinterpret_cast<uintptr_t>(out) % sizeof(OT)) == 0) {
+    pack_block(in, head, g, out);
+    i = head;
+    alignas(16) OT tmp[BLK];
+    for (; i + BLK <= n; i += BLK) {
+      pack_block(in + i, BLK, g, tmp);
+      for (int64_t k = 0; k < BLK; k += V)
+        _mm_stream_si128(reinterpret_cast<__m128i*>(out + i + k), _mm_load_si128(reinterpret_cast<const __m128i*>(tmp + k)));
+    }
+    _mm_sfence();
+  }
+#endif
+  pack_block(in + i, n - i, g, out + i);
 }
 
 __global__ void __launch_bounds__(256)

@@ -93,7 +93,10 @@ _pack_pool: ThreadPoolExecutor | None = None
 def _pool(world: int) -> ThreadPoolExecutor:
     global _pack_pool
     if _pack_pool is None:
-        _pack_pool = ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 1) // max(world, 1))),
+        # the pack is bound by host memory bandwidth: on the B200 box 16 threads are the optimum (107 ms per 8 GB of
+        # int64 labels; 32 threads 131 ms, 128 threads 307 ms — tools/e2e_probe.py)
+        want = int(os.environ.get("FLOXB_PACK_THREADS", "16"))
+        _pack_pool = ThreadPoolExecutor(max_workers=max(1, min(want, (os.cpu_count() or 1) // max(world, 1))),
                                         thread_name_prefix="floxb-pack")
     return _pack_pool
 

@@ -26,6 +26,8 @@ ncukexp)
       python tools/kbench.py 268435456 > gpurun_out/ncu_kexp.log 2>&1 ;;
 kbench3)
   timeout 600 python tools/kbench3.py > gpurun_out/kbench3.log 2>&1 ;;
+e2eprobe)
+  timeout 600 python tools/e2e_probe.py > gpurun_out/e2e_probe.log 2>&1 ;;
 kbench2)
   timeout 600 python tools/kbench2.py > gpurun_out/kbench2.log 2>&1 ;;
 configs)
