@@ -212,6 +212,40 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row
   }
 }
 
+// Grid-stride walk over the flat elements j = i*B + b of one `values[n, B]` slab for the L2-atomic kernels, U
+// elements per thread per step: all U (code, value) loads are issued before the first `apply(value, code, i, b)`,
+// so U loads are in flight per thread.  (ncu r01 on config 4, one element per step: nothing above 41% busy, 29
+// cycles of long-scoreboard stall per issue — pure load latency.)  (i, b) advance incrementally: one 64-bit
+// division per thread, not per element.  Elements whose code is outside [0, G) are skipped.
+template <int U, typename VT, typename CT, typename Apply>
+__device__ __forceinline__ void walk_flat(const VT* __restrict__ row, const CT* __restrict__ codes, int64_t row_len, int64_t B,
+                                          int64_t G, Apply apply) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = j / B, b = j - (j / B) * B;
+  const int64_t di = stride / B, db = stride - (stride / B) * B;
+  while (j < row_len) {
+    VT v[U];
+    CT c[U];
+    int64_t ii[U], bb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = j < row_len;
+      ii[u] = i;
+      bb[u] = b;
+      c[u] = ok ? codes[i] : (CT)-1;
+      v[u] = ok ? row[j] : VT(0);
+      j += stride;
+      i += di;
+      b += db;
+      if (b >= B) { b -= B; ++i; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if ((unsigned long long)c[u] < (unsigned long long)G) apply(v[u], c[u], ii[u], bb[u]);
+  }
+}
+
 // Host side: fill `tab` with chunks [c0, c0 + m) and return the number of tiles (of `tile` rows) they hold, or a
 // negative FLOXB_E* code.
 inline int64_t fill_chunk_table(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t c0, int64_t tile, ChunkTable* tab) {

@@ -76,18 +76,8 @@ k_minmax_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
                 long long* __restrict__ gkey, unsigned long long* __restrict__ gcnt,
                 unsigned long long* __restrict__ gnan) {
   const int64_t row_len = n * B;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
-    const VT* __restrict__ row = vals + a * row_len;
-    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
-    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
-    const int64_t di = stride / B, db = stride - (stride / B) * B;
-    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
-      if (b >= B) { b -= B; ++i; }
-      const CT c = codes[i];
-      if ((unsigned long long)c >= (unsigned long long)G) continue;
-      const VT v = row[j];
+    walk_flat<4>(vals + a * row_len, codes, row_len, B, G, [&](VT v, CT c, int64_t, int64_t b) {
       const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
       if (is_nan(v)) {
         atomicAdd(&gnan[bin], 1ull);
@@ -95,7 +85,7 @@ k_minmax_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
         key_update<long long, IS_MAX>(&gkey[bin], (long long)Key<VT>::enc(v));
         atomicAdd(&gcnt[bin], 1ull);
       }
-    }
+    });
   }
 }
 

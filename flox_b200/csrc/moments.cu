@@ -251,18 +251,8 @@ k_moments_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int6
                  unsigned long long* __restrict__ gnan) {
   using AccT = typename Acc<VT>::type;
   const int64_t row_len = n * B;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
-    const VT* __restrict__ row = vals + a * row_len;
-    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
-    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
-    const int64_t di = stride / B, db = stride - (stride / B) * B;
-    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
-      if (b >= B) { b -= B; ++i; }
-      const CT c = codes[i];
-      if ((unsigned long long)c >= (unsigned long long)G) continue;
-      const VT v = row[j];
+    walk_flat<4>(vals + a * row_len, codes, row_len, B, G, [&](VT v, CT c, int64_t, int64_t b) {
       // kept trailing dims: accumulators are GROUP-MAJOR [G][A*B], so the B values of one row land in one
       // contiguous run (tools/kbench2.py: 2.6x the L2 atomic rate of the [A*B][G] layout at G = 1e5)
       const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;
@@ -273,7 +263,7 @@ k_moments_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int6
         else atomic_add(&gacc[bin], lift<VT, OP>(v));
         atomicAdd(&gcnt[bin], 1ull);
       }
-    }
+    });
   }
 }
 

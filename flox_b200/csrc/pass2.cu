@@ -78,22 +78,38 @@ __global__ void __launch_bounds__(256)
 k_sqdev_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
                const double* __restrict__ means, int skipna, double* __restrict__ gm2) {
   const int64_t row_len = n * B;
+  constexpr int U = 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
     const VT* __restrict__ row = vals + a * row_len;
-    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
-    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
+    // three phases per step so that U value loads, then U mean loads, are in flight together (see walk_flat)
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = j / B, b = j - (j / B) * B;
     const int64_t di = stride / B, db = stride - (stride / B) * B;
-    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
-      if (b >= B) { b -= B; ++i; }
-      const CT c = codes[i];
-      if ((unsigned long long)c >= (unsigned long long)G) continue;
-      const VT v = row[j];
-      if (is_nan(v) && skipna) continue;
-      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
-      const double d = (double)v - means[bin];
-      atomicAdd(&gm2[bin], d * d);
+    while (j < row_len) {
+      VT v[U];
+      int64_t bin[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = j < row_len;
+        const CT c = ok ? codes[i] : (CT)-1;
+        v[u] = ok ? row[j] : VT(0);
+        const bool in = (unsigned long long)c < (unsigned long long)G;
+        bin[u] = !in ? -1 : (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
+        j += stride;
+        i += di;
+        b += db;
+        if (b >= B) { b -= B; ++i; }
+      }
+      double m[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) m[u] = (bin[u] >= 0 && !(is_nan(v[u]) && skipna)) ? means[bin[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (bin[u] < 0 || (is_nan(v[u]) && skipna)) continue;
+        const double d = (double)v[u] - m[u];
+        atomicAdd(&gm2[bin[u]], d * d);
+      }
     }
   }
 }
@@ -105,24 +121,14 @@ k_argext_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
                 const long long* __restrict__ key, const long long* __restrict__ nnan, int skipna, int64_t index_base,
                 long long* __restrict__ gidx) {
   const int64_t row_len = n * B;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
-    const VT* __restrict__ row = vals + a * row_len;
-    // (row i, kept column b) of flat element j, advanced incrementally: one 64-bit division per thread, not per element
-    const int64_t j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t i = j0 / B, b = j0 - (j0 / B) * B;
-    const int64_t di = stride / B, db = stride - (stride / B) * B;
-    for (int64_t j = j0; j < row_len; j += stride, i += di, b += db) {
-      if (b >= B) { b -= B; ++i; }
-      const CT c = codes[i];
-      if ((unsigned long long)c >= (unsigned long long)G) continue;
-      const VT v = row[j];
+    walk_flat<4>(vals + a * row_len, codes, row_len, B, G, [&](VT v, CT c, int64_t i, int64_t b) {
       const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;  // group-major when B > 1
       bool hit;
       if (!skipna && nnan[bin] > 0) hit = is_nan(v);          // NaN propagates: first NaN wins
       else hit = !is_nan(v) && (long long)Key<VT>::enc(v) == key[bin];
       if (hit) atomicMin(&gidx[bin], (long long)(index_base + i));
-    }
+    });
   }
 }
 

@@ -26,6 +26,9 @@ ncukexp)
       python tools/kbench.py 268435456 > gpurun_out/ncu_kexp.log 2>&1 ;;
 kbench3)
   timeout 600 python tools/kbench3.py > gpurun_out/kbench3.log 2>&1 ;;
+ncuother)
+  timeout 1200 ncu --set full --clock-control none --import-source on -k 'regex:k_moments_global|k_rows|k_sqdev_global' -c 8 -f -o gpurun_out/prof_other \
+      python tools/configs_bench.py c4 c5 rows > gpurun_out/ncu_other.log 2>&1 ;;
 e2eprobe)
   timeout 600 python tools/e2e_probe.py > gpurun_out/e2e_probe.log 2>&1 ;;
 kbench2)
