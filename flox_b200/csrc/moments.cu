@@ -299,39 +299,51 @@ k_moments_global_runs(const VT* __restrict__ vals, const CT* __restrict__ codes,
     const int64_t warp_span = 32;
     const int64_t nvec_full = aligned ? (nvec / warp_span) * warp_span : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec_full; q += stride) {
-      const Vec4<VT> v = load4<VT>(row + q * 4);
-      const Vec4<CT> c = load4<CT>(codes + q * 4);
-      long long cur = (long long)c.v[0];
-      AccT s = ident;
-      unsigned cn = 0, mn = 0;
-      bool single = true;
+    // two vectors per thread per step, both loaded before either is merged: twice the loads in flight
+    auto merge_vec = [&](const Vec4<VT>& v, const Vec4<CT>& c) {
+        long long cur = (long long)c.v[0];
+        AccT s = ident;
+        unsigned cn = 0, mn = 0;
+        bool single = true;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const long long ck = (long long)c.v[k];
-        if (ck != cur) {
-          flush(cur, s, cn, mn);
-          cur = ck; s = ident; cn = 0; mn = 0; single = false;
-        }
-        if (is_nan(v.v[k])) mn++; else { s = merge(s, lift<VT, OP>(v.v[k])); cn++; }
-      }
-      int uniform;
-      __match_all_sync(0xffffffffu, cur, &uniform);
-      const bool warp_one = __all_sync(0xffffffffu, single) && uniform;
-      if (warp_one) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          if constexpr (sizeof(AccT) == 8) {
-            const long long o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long*>(&s), d);
-            s = merge(s, *reinterpret_cast<const AccT*>(&o));
+        for (int k = 0; k < 4; ++k) {
+          const long long ck = (long long)c.v[k];
+          if (ck != cur) {
+            flush(cur, s, cn, mn);
+            cur = ck; s = ident; cn = 0; mn = 0; single = false;
           }
-          cn += __shfl_xor_sync(0xffffffffu, cn, d);
-          mn += __shfl_xor_sync(0xffffffffu, mn, d);
+          if (is_nan(v.v[k])) mn++; else { s = merge(s, lift<VT, OP>(v.v[k])); cn++; }
         }
-        if ((threadIdx.x & 31) == 0) flush(cur, s, cn, mn);
-      } else {
-        flush(cur, s, cn, mn);
+        int uniform;
+        __match_all_sync(0xffffffffu, cur, &uniform);
+        const bool warp_one = __all_sync(0xffffffffu, single) && uniform;
+        if (warp_one) {
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            if constexpr (sizeof(AccT) == 8) {
+              const long long o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long*>(&s), d);
+              s = merge(s, *reinterpret_cast<const AccT*>(&o));
+            }
+            cn += __shfl_xor_sync(0xffffffffu, cn, d);
+            mn += __shfl_xor_sync(0xffffffffu, mn, d);
+          }
+          if ((threadIdx.x & 31) == 0) flush(cur, s, cn, mn);
+        } else {
+          flush(cur, s, cn, mn);
+        }
+    };
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec_full; q += 2 * stride) {
+      const bool two = q + stride < nvec_full;  // warp-uniform: nvec_full and stride are multiples of 32
+      const Vec4<VT> v0 = load4<VT>(row + q * 4);
+      const Vec4<CT> c0 = load4<CT>(codes + q * 4);
+      Vec4<VT> v1;
+      Vec4<CT> c1;
+      if (two) {
+        v1 = load4<VT>(row + (q + stride) * 4);
+        c1 = load4<CT>(codes + (q + stride) * 4);
       }
+      merge_vec(v0, c0);
+      if (two) merge_vec(v1, c1);
     }
     // scalar remainder (unaligned chunks, n % 128 tail)
     for (int64_t i = nvec_full * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
