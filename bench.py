@@ -404,8 +404,9 @@ def run_gpu(args):
                "d2h_bytes_per_step": world * int(out.numel() * out.element_size()), "ms_per_step": dt * 1e3,
                "steps": args.e2e_steps, "host_bytes_per_step": world * rows * BYTES_PER_ROW,
                "how": "pinned host chunks (f32 values + int64 labels) -> groupby_reduce(ChunkedArray, method='map-reduce') -> host "
-                      "result; labels are range-checked and narrowed to int16 by host threads on the way to the pinned "
-                      "staging buffers (6 instead of 12 bytes per row cross PCIe)"}
+                      "result; " + ("labels are range-checked and narrowed to int16 by host threads on the way to the pinned "
+                                    "staging buffers (6 instead of 12 bytes per row cross PCIe)" if world == 1 else
+                                    "several ranks per host: labels are copied as int64 (host label packing is single-rank only)")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

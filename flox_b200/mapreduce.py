@@ -119,7 +119,11 @@ def _stage_packed_codes(label_chunks: dict, n_groups: int, device, world: int) -
     PCIe when the groups fit 16 (32) bits: worker threads range-check + narrow each chunk into a pinned staging
     buffer (floxb_host_pack_codes), the copies are enqueued as the packs finish, int16 is widened on the device
     (floxb_widen_codes).  Returns {chunk index: device codes}; chunks it does not take are left to the caller."""
-    if device.type != "cuda" or n_groups > 2**31 - 1:
+    policy = os.environ.get("FLOXB_PACK_LABELS", "auto")
+    # The pack is bound by what the HOST can stream (~77 GB/s of label reads on the B200 box however many threads
+    # or processes share it: profiles/r01_e2e_probe_session19.log, r01_bench_4gpu.log), so with several ranks per
+    # host it is slower than letting every rank's own PCIe link copy the int64 labels: auto = single rank only.
+    if device.type != "cuda" or n_groups > 2**31 - 1 or policy == "0" or (policy == "auto" and world > 1):
         return {}
     todo = {}
     for k, c in label_chunks.items():
