@@ -250,21 +250,26 @@ def test_time_major_layout_column_kernels(dtype):
         assert_same(got_t.cpu().numpy(), want, what=f"cols-torch/{func}/{np.dtype(dtype)}", **_tols(func, base))
 
 
+@pytest.mark.parametrize("ngroups", [13, 40])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
-def test_row_batched_layout_warp_per_row_kernels(dtype):
-    """(lat*lon, time) rows sharing one label vector — the layout flox's own reshape produces."""
+def test_row_batched_layout_warp_per_row_kernels(dtype, ngroups):
+    """(lat*lon, time) rows sharing one label vector — the layout flox's own reshape produces.  13 groups take the
+    lane-private-bin kernel (k_rows_bins, G <= 32), 40 groups the permutation kernel (k_rows)."""
     rng = np.random.default_rng(21)
     A, T = 700, 3650
     arr = (rng.random((A, T)) * 10 - 2).astype(dtype)
     if np.dtype(dtype).kind == "f":
         arr[5, rng.random(T) < 0.1] = np.nan
         arr[6, :] = np.nan
-    months = ((np.arange(T) % 365) // 30.42).astype(np.int64).clip(0, 11)
-    months[::400] = -1
+    if ngroups == 13:
+        labels = ((np.arange(T) % 365) // 30.42).astype(np.int64).clip(0, 11)
+    else:
+        labels = ((np.arange(T) % 365) // 9.4).astype(np.int64).clip(0, 38)
+    labels[::400] = -1
     for func in ("sum", "nanmean", "max", "nanmin", "count", "nanvar"):
-        want, _ = O.groupby_reduce(arr, months, func=func, expected_groups=np.arange(13))
-        got, _ = flox_b200.groupby_reduce(arr, months, func=func, expected_groups=np.arange(13))
-        assert_same(got, want, what=f"rows/{func}/{np.dtype(dtype)}", **_tols(func, arr))
+        want, _ = O.groupby_reduce(arr, labels, func=func, expected_groups=np.arange(ngroups))
+        got, _ = flox_b200.groupby_reduce(arr, labels, func=func, expected_groups=np.arange(ngroups))
+        assert_same(got, want, what=f"rows/{func}/{np.dtype(dtype)}/{ngroups}", **_tols(func, arr))
 
 
 def test_torch_cuda_inputs_stay_on_device():
