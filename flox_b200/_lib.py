@@ -49,6 +49,9 @@ SIGNATURES = {
     "floxb_var_combine": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "floxb_digitize": (_i32, [_vp, _i32, _i64, _vp, _i64, _i32, _vp, _vp]),
     "floxb_ravel_codes": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "floxb_label_minmax": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "floxb_label_presence": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "floxb_lut_codes": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "floxb_host_pack_codes": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32]),
     "floxb_widen_codes": (_i32, [_vp, _i64, _vp, _vp]),
 }

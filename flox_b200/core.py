@@ -407,6 +407,8 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
 
     bys = tuple(b if (is_torch(b) or is_chunked(b)) else np.asarray(b) for b in by)
     nby = len(bys)
+    # pandas widens datetime64[D] / [h] / [m] labels to [s]; discovered groups are handed back in the labels' own unit
+    by_datetime_units = {i: b.dtype for i, b in enumerate(bys) if isinstance(b, np.ndarray) and b.dtype.kind == "M"}
     by_is_chunked = tuple(is_chunked(b) for b in bys)
     any_by_chunked = any(by_is_chunked)
     provided_expected = expected_groups is not None
@@ -518,4 +520,7 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
         np.arange(len(g), dtype=arange_like[i]) if i in arange_like
         else (g.to_numpy() if isinstance(g, pd.Index) and not isinstance(g, pd.RangeIndex) else g)
         for i, g in enumerate(groups))
+    if by_datetime_units and not provided_expected:
+        groups = tuple(g.astype(by_datetime_units[i]) if i in by_datetime_units and isinstance(g, np.ndarray)
+                       and g.dtype.kind == "M" and g.dtype != by_datetime_units[i] else g for i, g in enumerate(groups))
     return (result, *groups)

@@ -58,9 +58,105 @@ k_widen_codes(const short4* __restrict__ in4, const int16_t* __restrict__ in, in
   for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
 }
 
+// ---- discovery of unknown integer labels -----------------------------------------------------------------
+__global__ void k_minmax_init(long long* mm) {
+  mm[0] = INT64_MAX;
+  mm[1] = INT64_MIN;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_label_minmax(const CT* __restrict__ labels, int64_t n, long long* __restrict__ mm) {
+  long long lo = INT64_MAX, hi = INT64_MIN;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long c = (long long)labels[i];
+    lo = c < lo ? c : lo;
+    hi = c > hi ? c : hi;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, lo, d), b = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], lo);
+    atomicMax(&mm[1], hi);
+  }
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_label_presence(const CT* __restrict__ labels, int64_t n, long long lo, unsigned long long range, uint8_t* __restrict__ table) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long rel = (unsigned long long)((long long)labels[i] - lo);
+    if (rel < range && !table[rel]) table[rel] = 1;  // benign race: every writer stores the same byte
+  }
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(256)
+k_lut_codes(const CT* __restrict__ labels, int64_t n, long long lo, unsigned long long range, const long long* __restrict__ lut,
+            long long* __restrict__ codes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long rel = (unsigned long long)((long long)labels[i] - lo);
+    codes[i] = rel < range ? lut[rel] : -1ll;
+  }
+}
+
+static inline unsigned label_blocks(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (b > cap) b = cap;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
 }  // namespace floxb
 
 using namespace floxb;
+
+extern "C" int floxb_label_minmax(const void* labels, int label_dtype, int64_t n, int64_t* minmax, void* stream) {
+  if (n <= 0 || !labels || !minmax) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto* mm = reinterpret_cast<long long*>(minmax);
+  k_minmax_init<<<1, 1, 0, st>>>(mm);
+  if (label_dtype == FLOXB_I64) k_label_minmax<<<label_blocks(n), 256, 0, st>>>(static_cast<const int64_t*>(labels), n, mm);
+  else if (label_dtype == FLOXB_I32) k_label_minmax<<<label_blocks(n), 256, 0, st>>>(static_cast<const int32_t*>(labels), n, mm);
+  else return FLOXB_EDTYPE;
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+extern "C" int floxb_label_presence(const void* labels, int label_dtype, int64_t n, int64_t lo, int64_t range,
+                                    uint8_t* table, void* stream) {
+  if (n < 0 || range < 0) return FLOXB_EINVAL;
+  if (range == 0) return FLOXB_OK;
+  if (!table || (n > 0 && !labels)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(table, 0, (size_t)range, st) != cudaSuccess) return FLOXB_ECUDA;
+  if (n == 0) return FLOXB_OK;
+  if (label_dtype == FLOXB_I64)
+    k_label_presence<<<label_blocks(n), 256, 0, st>>>(static_cast<const int64_t*>(labels), n, (long long)lo, (unsigned long long)range, table);
+  else if (label_dtype == FLOXB_I32)
+    k_label_presence<<<label_blocks(n), 256, 0, st>>>(static_cast<const int32_t*>(labels), n, (long long)lo, (unsigned long long)range, table);
+  else return FLOXB_EDTYPE;
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+extern "C" int floxb_lut_codes(const void* labels, int label_dtype, int64_t n, int64_t lo, int64_t range, const int64_t* lut,
+                               int64_t* codes, void* stream) {
+  if (n < 0 || range < 0) return FLOXB_EINVAL;
+  if (n == 0) return FLOXB_OK;
+  if (!labels || !codes || (range > 0 && !lut)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto* l = reinterpret_cast<const long long*>(lut);
+  auto* c = reinterpret_cast<long long*>(codes);
+  if (label_dtype == FLOXB_I64)
+    k_lut_codes<<<label_blocks(n), 256, 0, st>>>(static_cast<const int64_t*>(labels), n, (long long)lo, (unsigned long long)range, l, c);
+  else if (label_dtype == FLOXB_I32)
+    k_lut_codes<<<label_blocks(n), 256, 0, st>>>(static_cast<const int32_t*>(labels), n, (long long)lo, (unsigned long long)range, l, c);
+  else return FLOXB_EDTYPE;
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
 
 extern "C" int floxb_host_pack_codes(const void* codes, int code_dtype, int64_t n, int64_t n_groups, void* out, int out_bits) {
   if (n < 0 || n_groups < 0) return FLOXB_EINVAL;

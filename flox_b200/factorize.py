@@ -91,9 +91,11 @@ class IntLabelEncoder:
         lut = self._lut.get(flat.device)
         if lut is None:
             lut = self._lut[flat.device] = torch.as_tensor(self._table, device=flat.device)
-        rel = flat.to(torch.int64) - self.lo
-        inside = (rel >= 0) & (rel <= self.hi - self.lo)
-        return torch.where(inside, lut[rel.clamp(0, self.hi - self.lo)], rel.new_full((), -1))
+        src = flat if flat.dtype in (torch.int32, torch.int64) else flat.to(torch.int64)
+        src = src.contiguous()
+        codes = torch.empty(src.numel(), dtype=torch.int64, device=src.device)
+        get_kernels().lut_codes(src, self.lo, lut, codes)
+        return codes.reshape(flat.shape)
 
 
 _last_encoder: tuple = (None, None, None)
@@ -108,11 +110,59 @@ def int_label_encoder(expect: pd.Index, sort: bool) -> IntLabelEncoder:
     return enc
 
 
+_DISCOVER_MAX_SPAN = 1 << 26  # presence table of at most 64 MiB
+
+
+def _discover_int_labels(by):
+    """Unknown integer (or datetime) labels: sorted unique values and codes WITHOUT the host hash pass of
+    pd.factorize (flox/factorize.py:95-99): min/max -> presence table over [min, max] -> groups = min + nonzero(table)
+    -> codes through a lookup table, all on the device (floxb_label_minmax / _presence / _lut_codes).  Returns None
+    when it does not apply (non-integer labels, empty input, value span above 2^26)."""
+    np_dt = None
+    if is_torch(by):
+        if by.dtype not in (torch.int8, torch.int16, torch.int32, torch.int64, torch.uint8) or by.numel() == 0:
+            return None
+        dev = by.reshape(-1)
+    else:
+        a = np.asarray(by)
+        if a.dtype.kind not in "iuM" or a.size == 0 or (a.dtype.kind == "u" and a.dtype.itemsize == 8):
+            return None
+        np_dt = a.dtype
+        dev = to_device(a.reshape(-1))   # datetime64 -> int64 view, small unsigned -> int64
+    if dev.dtype not in (torch.int32, torch.int64):
+        dev = dev.to(torch.int64)
+    dev = dev.contiguous()
+    kern = get_kernels()
+    lo, hi = kern.label_minmax(dev)
+    if np_dt is not None and np_dt.kind == "M" and lo == np.iinfo(np.int64).min:
+        return None  # NaT labels: leave the null handling to the host path
+    span = hi - lo + 1
+    if span > _DISCOVER_MAX_SPAN:
+        return None
+    present = kern.label_presence(dev, lo, span).cpu().numpy()
+    rel = np.flatnonzero(present)
+    lut_np = np.full(span, -1, dtype=np.int64)
+    lut_np[rel] = np.arange(rel.size)
+    codes = torch.empty(dev.numel(), dtype=torch.int64, device=dev.device)
+    kern.lut_codes(dev, lo, torch.as_tensor(lut_np, device=dev.device), codes)
+    values = rel.astype(np.int64) + lo
+    if np_dt is not None:
+        values = values.view(np_dt) if np_dt.kind == "M" else values.astype(np_dt)
+    elif is_torch(by) and by.dtype != torch.int64:
+        values = values.astype(np.dtype(str(by.dtype).replace("torch.", "")))
+    return pd.Index(values), codes
+
+
 def _factorize_single(by, expect, *, sort: bool, reindex: bool):
     """(groups Index, codes shaped like `by`) for one grouper (factorize.py:42-99)."""
     shape = tuple(by.shape)
     on_device = is_torch(by)
     flat = by.reshape(-1)
+    if expect is None and sort:
+        found = _discover_int_labels(by)
+        if found is not None:
+            groups, codes = found
+            return groups, (codes if on_device else codes.cpu().numpy()).reshape(shape)
     if on_device and not flat.dtype.is_floating_point and flat.dtype != torch.bool and _is_int_index(expect):
         enc = int_label_encoder(expect, sort)
         if enc.mode is not None:

@@ -240,6 +240,34 @@ class CudaKernels:
         self.launches += 1
         self.kernel_launches += 1
 
+    def label_minmax(self, labels) -> tuple[int, int]:
+        """(min, max) of a non-empty integer label tensor (one 16-byte D2H read)."""
+        self._require_cuda(labels)
+        mm = torch.empty(2, dtype=torch.int64, device=labels.device)
+        L.check(L.load().floxb_label_minmax(self._ptr(labels), dtype_code(labels.dtype), labels.numel(), self._ptr(mm), self._stream()),
+                "floxb_label_minmax")
+        self.launches += 1
+        self.kernel_launches += 2
+        lo, hi = mm.tolist()
+        return int(lo), int(hi)
+
+    def label_presence(self, labels, lo: int, span: int) -> torch.Tensor:
+        """u8[span]: 1 where lo + k occurs in `labels`."""
+        self._require_cuda(labels)
+        table = torch.empty(span, dtype=torch.uint8, device=labels.device)
+        L.check(L.load().floxb_label_presence(self._ptr(labels), dtype_code(labels.dtype), labels.numel(), lo, span, self._ptr(table),
+                                              self._stream()), "floxb_label_presence")
+        self.launches += 1
+        self.kernel_launches += 1 if labels.numel() else 0
+        return table
+
+    def lut_codes(self, labels, lo: int, lut, codes) -> None:
+        self._require_cuda(labels, lut, codes)
+        L.check(L.load().floxb_lut_codes(self._ptr(labels), dtype_code(labels.dtype), labels.numel(), lo, lut.numel(), self._ptr(lut),
+                                         self._ptr(codes), self._stream()), "floxb_lut_codes")
+        self.launches += 1
+        self.kernel_launches += 1 if labels.numel() else 0
+
     def smem_group_limit(self, value_dtype, family: int) -> int:
         return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))
 

@@ -186,6 +186,20 @@ int floxb_digitize(const void* labels, int label_dtype, int64_t n, const double*
 int floxb_ravel_codes(const int64_t* c0, const int64_t* c1, int64_t n, int64_t size0, int64_t size1,
                       int64_t* out, void* stream);
 
+/* Discovery of UNKNOWN integer labels on the device (expected_groups=None: the reference runs pd.factorize on
+ * the host, flox/factorize.py:95-99, a hash pass of ~5 ns per label):
+ *   floxb_label_minmax   : minmax[0] = min(labels), minmax[1] = max(labels)   (device int64[2]; n > 0)
+ *   floxb_label_presence : table[labels[i] - lo] = 1 for lo <= labels[i] < lo + range   (table: device u8[range],
+ *                          zeroed by the call).  The sorted unique labels are lo + nonzero(table).
+ *   floxb_lut_codes      : codes[i] = lut[labels[i] - lo] if lo <= labels[i] < lo + range else -1 — also the
+ *                          searchsorted + isin of known integer groups (factorize.py:84-94).
+ * label_dtype FLOXB_I32 / FLOXB_I64. */
+int floxb_label_minmax(const void* labels, int label_dtype, int64_t n, int64_t* minmax, void* stream);
+int floxb_label_presence(const void* labels, int label_dtype, int64_t n, int64_t lo, int64_t range,
+                         uint8_t* table, void* stream);
+int floxb_lut_codes(const void* labels, int label_dtype, int64_t n, int64_t lo, int64_t range,
+                    const int64_t* lut, int64_t* codes, void* stream);
+
 /* Label staging for host-resident chunks.  flox hands every block int64 codes (flox/factorize.py:201-210,
  * flox/core.py:298-316); over PCIe they are 2/3 of the bytes of an f32 reduction.  When n_groups < 2^15 (2^31) the
  * codes fit 16 (32) bits:

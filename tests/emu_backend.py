@@ -296,6 +296,24 @@ class EmuKernels:
         bad = (a < 0) | (b < 0) | (a >= size0) | (b >= size1)
         _np(out)[...] = np.where(bad, -1, a * size1 + b)
 
+    def label_minmax(self, labels):
+        self.launches += 1
+        a = _np(labels)
+        return int(a.min()), int(a.max())
+
+    def label_presence(self, labels, lo, span):
+        self.launches += 1
+        rel = _np(labels).astype(np.int64) - lo
+        table = np.zeros(span, dtype=np.uint8)
+        table[rel[(rel >= 0) & (rel < span)]] = 1
+        return torch.from_numpy(table)
+
+    def lut_codes(self, labels, lo, lut, codes):
+        self.launches += 1
+        rel = _np(labels).astype(np.int64) - lo
+        inside = (rel >= 0) & (rel < lut.numel())
+        _np(codes)[...] = np.where(inside, _np(lut)[np.clip(rel, 0, max(lut.numel() - 1, 0))] if lut.numel() else -1, -1)
+
     def smem_group_limit(self, value_dtype, family):
         return 14000
 

@@ -194,6 +194,25 @@ def test_host_label_staging(ngroups, label_dtype):
         assert moved == N * (4 + packed), (moved, N, packed)
 
 
+@pytest.mark.parametrize("container", ["numpy", "cuda"])
+@pytest.mark.parametrize("label_dtype", [np.int64, np.int32])
+def test_unknown_integer_labels_discovered_on_device(label_dtype, container):
+    """expected_groups=None (BASELINE config 1's call): groups and codes from floxb_label_minmax / _presence /
+    floxb_lut_codes instead of a host pd.factorize; groups, order and results equal the reference's."""
+    rng = np.random.default_rng(17)
+    N = 1_000_003
+    x = rng.random(N).astype(np.float32)
+    by = (rng.integers(0, 100, N) * 3 - 50).astype(label_dtype)   # 100 groups, non-contiguous values, negative ones too
+    xa, ba = (x, by) if container == "numpy" else (torch.as_tensor(x, device="cuda"), torch.as_tensor(by, device="cuda"))
+    for func in ("sum", "nanmean", "count", "max"):
+        got, groups = flox_b200.groupby_reduce(xa, ba, func=func)
+        want, want_groups = O.groupby_reduce(x, by, func=func)
+        got = got.cpu().numpy() if isinstance(got, torch.Tensor) else got
+        groups = np.asarray(groups)
+        assert groups.dtype == np.asarray(want_groups).dtype and np.array_equal(groups, np.asarray(want_groups))
+        assert_same(got, want, what=f"discover/{func}/{container}", **_tols(func, x))
+
+
 @pytest.mark.parametrize("func", ["argmax", "argmin", "nanargmax", "nanargmin"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
 def test_arg_reductions(func, dtype):

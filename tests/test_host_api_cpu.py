@@ -67,3 +67,42 @@ def test_engine_functions_match_reference(case, emu):  # noqa: F811
     r64 = RTOL32 if arr.dtype == np.float32 else RTOL64
     assert_same(res, want, what=case["id"], rtol_f32=RTOL32, rtol_f64=r64,
                 atol_f32=cond_atol(case["func"], arr, RTOL32), atol_f64=cond_atol(case["func"], arr, r64))
+
+
+@pytest.mark.parametrize("label_dtype", ["int64", "int32", "uint8", "int16", "datetime64[D]", "datetime64[ns]"])
+def test_unknown_integer_labels_are_discovered_without_a_host_hash(label_dtype, emu):  # noqa: F811
+    """expected_groups=None with integer / datetime labels: groups and codes come from the min/max -> presence
+    table -> lookup-table kernels (flox_b200/factorize.py:_discover_int_labels), not from pd.factorize; the
+    groups (values, order, dtype) and results must equal the reference's (oracle, flox/factorize.py:95-99)."""
+    from flox_b200 import factorize
+    from oracle import flox_oracle as O
+
+    rng = np.random.default_rng(8)
+    x = rng.random(5000).astype(np.float32)
+    if label_dtype.startswith("datetime"):
+        base = np.datetime64("2001-03-01").astype(label_dtype)
+        by = base + rng.integers(-40, 40, 5000).astype("timedelta64[D]").astype(f"timedelta64[{label_dtype[11:-1]}]")
+    else:
+        lo = 0 if label_dtype == "uint8" else -7
+        by = rng.integers(lo, 90, 5000).astype(label_dtype)
+    calls = []
+    orig = factorize._discover_int_labels
+    factorize._discover_int_labels = lambda b: calls.append(1) or orig(b)
+    try:
+        for func in ("sum", "nanmax", "count"):
+            got, groups = flox_b200.groupby_reduce(x, by, func=func)
+            want, want_groups = O.groupby_reduce(x, by, func=func)
+            want_groups = np.asarray(want_groups)
+            assert groups.dtype == want_groups.dtype and np.array_equal(groups, want_groups)
+            assert_same(got, want, what=f"discover/{label_dtype}/{func}", rtol_f32=RTOL32, rtol_f64=RTOL64)
+    finally:
+        factorize._discover_int_labels = orig
+    assert len(calls) == 3
+    # a value span above 2^26 falls back to the host path and still matches
+    wide = by.astype("int64").copy() if not label_dtype.startswith("datetime") else None
+    if wide is not None:
+        wide[0] = 2**40
+        got, groups = flox_b200.groupby_reduce(x, wide, func="sum")
+        want, want_groups = O.groupby_reduce(x, wide, func="sum")
+        assert np.array_equal(groups, np.asarray(want_groups))
+        assert_same(got, want, what="discover/wide", rtol_f32=RTOL32, rtol_f64=RTOL64)
