@@ -21,8 +21,14 @@ PEAK = 6570.3
 OUT = []
 
 
-def timeit(fn, reps=5, warm=2):
+def timeit(fn, reps=5, warm=2, spin_s=0.4):
     for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    # steady state: keep the GPU busy for ~0.4 s first.  After an idle gap (data generation, host work) the
+    # first calls run up to 2.4x slower (C5 alone: 3.4-4.1 ms against 1.65 ms when it follows other configs).
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < spin_s:
         fn()
     torch.cuda.synchronize()
     ts = []
@@ -48,6 +54,9 @@ def main():
     which = sys.argv[1:] or ["c1", "c3", "c4", "c5", "rows"]
     dev = torch.device("cuda")
     gen = torch.Generator(device=dev).manual_seed(12345)
+    # placement experiment: FLOXB_BENCH_PAD_MB shifts every later allocation by that many MiB
+    pad_mb = int(os.environ.get("FLOXB_BENCH_PAD_MB", "0"))
+    pad = torch.empty(pad_mb << 20, dtype=torch.uint8, device=dev) if pad_mb else None  # noqa: F841
 
     if "c1" in which:
         n, G = 1_000_000, 100
