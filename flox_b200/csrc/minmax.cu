@@ -20,7 +20,6 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_minmax_smem(const __grid_constant__ ChunkTable tab, int G, long long* __restrict__ gkey,
               unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
   using K = typename Key<VT>::type;
-  constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int R = 1 << RSHIFT;
   const int S = G << RSHIFT;

@@ -58,7 +58,6 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
                typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
                unsigned long long* __restrict__ gnan) {
   using AccT = typename Acc<VT>::type;
-  constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using ST = typename Slot<VT, OP>::type;
   constexpr bool kPartial = Slot<VT, OP>::partial;
@@ -157,7 +156,6 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int G, double* __restrict__ gacc,
                    unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan,
                    double* __restrict__ workspace) {
-  constexpr int TILE = THREADS * 4 * ITERS;
   constexpr int R = 1 << RSHIFT;
   const int S = G << RSHIFT;
   const int NW = (G + 31) >> 5;
@@ -268,10 +266,10 @@ k_moments_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int6
 }
 
 // L2-atomic path specialised for B == 1: 4 rows per thread (128-bit loads), adjacent equal codes are
-// merged in registers, and a warp whose 128 rows all carry ONE code (sorted labels: BASELINE config 5,
-// method="cohorts") reduces with shuffles and issues a single set of atomics.  For sorted labels the
-// atomic traffic drops by ~128x and the kernel is a pure HBM stream; for random labels it degrades to
-// one atomic set per row like k_moments_global.
+// merged in registers, then RUNS of lanes that end in the same code are merged with a segmented shuffle
+// reduction and only the first lane of a run issues atomics.  For sorted labels (BASELINE config 5,
+// method="cohorts") a warp's 128 rows hold one or two groups: the atomic traffic drops by ~100x and the
+// kernel is an HBM stream; for random labels it degrades to one atomic set per row like k_moments_global.
 template <typename VT, typename CT, int OP>
 __global__ void __launch_bounds__(256)
 k_moments_global_runs(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t G,
@@ -304,33 +302,40 @@ k_moments_global_runs(const VT* __restrict__ vals, const CT* __restrict__ codes,
         long long cur = (long long)c.v[0];
         AccT s = ident;
         unsigned cn = 0, mn = 0;
-        bool single = true;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const long long ck = (long long)c.v[k];
           if (ck != cur) {
             flush(cur, s, cn, mn);
-            cur = ck; s = ident; cn = 0; mn = 0; single = false;
+            cur = ck; s = ident; cn = 0; mn = 0;
           }
           if (is_nan(v.v[k])) mn++; else { s = merge(s, lift<VT, OP>(v.v[k])); cn++; }
         }
-        int uniform;
-        __match_all_sync(0xffffffffu, cur, &uniform);
-        const bool warp_one = __all_sync(0xffffffffu, single) && uniform;
-        if (warp_one) {
+        // Segmented warp reduction over RUNS of lanes that end in the same group: one flush per run instead of
+        // one per lane.  With sorted labels a warp's 128 rows hold 1-2 groups, so it issues 1-2 sets of REDs; the
+        // earlier "whole warp uniform, else every lane flushes" left a quarter of the warps sending 32 REDs each
+        // to the same two addresses, and the kernel swung between 1.65 and 4.1 ms on same-address L2 serialisation.
+        // Random labels: every lane is its own run, nothing changes.
+        const unsigned lane = threadIdx.x & 31u;
+        const long long kprev = __shfl_up_sync(0xffffffffu, cur, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0u || kprev != cur);
+        const unsigned after = (heads >> lane) >> 1;  // head flags of lanes lane+1, lane+2, ...
 #pragma unroll
-          for (int d = 16; d > 0; d >>= 1) {
-            if constexpr (sizeof(AccT) == 8) {
-              const long long o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<long long*>(&s), d);
-              s = merge(s, *reinterpret_cast<const AccT*>(&o));
-            }
-            cn += __shfl_xor_sync(0xffffffffu, cn, d);
-            mn += __shfl_xor_sync(0xffffffffu, mn, d);
+        for (int d = 1; d < 32; d <<= 1) {
+          AccT s2;
+          if constexpr (sizeof(AccT) == 8) {
+            const long long o = __shfl_down_sync(0xffffffffu, *reinterpret_cast<long long*>(&s), d);
+            s2 = *reinterpret_cast<const AccT*>(&o);
           }
-          if ((threadIdx.x & 31) == 0) flush(cur, s, cn, mn);
-        } else {
-          flush(cur, s, cn, mn);
+          const unsigned cn2 = __shfl_down_sync(0xffffffffu, cn, d), mn2 = __shfl_down_sync(0xffffffffu, mn, d);
+          // lane+d belongs to this lane's run iff no run starts in (lane, lane+d]
+          if (lane + d < 32u && (after & ((1u << d) - 1u)) == 0u) {
+            s = merge(s, s2);
+            cn += cn2;
+            mn += mn2;
+          }
         }
+        if ((heads >> lane) & 1u) flush(cur, s, cn, mn);
     };
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nvec_full; q += 2 * stride) {
       const bool two = q + stride < nvec_full;  // warp-uniform: nvec_full and stride are multiples of 32

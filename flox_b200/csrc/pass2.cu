@@ -34,7 +34,6 @@ template <typename VT, typename CT, int THREADS, int ITERS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sqdev_smem(const __grid_constant__ ChunkTable tab, int G, const double* __restrict__ means,
              int skipna, double* __restrict__ gm2) {
-  constexpr int TILE = THREADS * 4 * ITERS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // f32 values: the group mean is f32-representable by construction (floxb_group_means rounds it
   // like the reference's f32 `array_sums / array_lens`), the deviation is formed exactly in f64,
