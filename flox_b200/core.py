@@ -193,7 +193,10 @@ def chunk_reduce(array, by, func, expected_groups, axis=None, fill_value=None, d
                 result = from_device(t.reshape(lead + (size,)), array, out_dt).reshape(out_shape)
         results["intermediates"].append(result)
         previous = reduction
-    results["groups"] = np.broadcast_to(np.asarray(results["groups"]), final_groups_shape)
+    if not (isinstance(results["groups"], pd.RangeIndex) and tuple(final_groups_shape) == (len(results["groups"]),)):
+        # a RangeIndex stays one (O(1)); materialising, copying and comparing 1e6 group labels on the host cost more
+        # per call than the reduction kernel of BASELINE config 5 (tools/c5_hostprofile.py)
+        results["groups"] = np.broadcast_to(np.asarray(results["groups"]), final_groups_shape)
     return results
 
 
@@ -222,7 +225,10 @@ def chunk_argreduce(array_plus_idx, by, func, expected_groups, axis, fill_value,
 
 def _squeeze_results(results: dict, axis) -> dict:
     groups = results["groups"]
-    out = {"groups": np.squeeze(groups, axis=tuple(ax for ax in range(groups.ndim - 1) if groups.shape[ax] == 1))}
+    if isinstance(groups, pd.RangeIndex):
+        out = {"groups": groups}
+    else:
+        out = {"groups": np.squeeze(groups, axis=tuple(ax for ax in range(groups.ndim - 1) if groups.shape[ax] == 1))}
     squeezed = []
     for v in results["intermediates"]:
         for ax in sorted((a for a in sorted(axis)[:-1] if v.shape[a] == 1), reverse=True):

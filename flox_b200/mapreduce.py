@@ -234,6 +234,6 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
 
     if not do_finalize:
         agg.finalize = None
-    results = {"groups": np.asarray(expected_groups), "intermediates": inter}
+    results = {"groups": expected_groups, "intermediates": inter}  # stays a RangeIndex: no O(G) host work
     final = _finalize_results(results, agg, axis, expected_groups, reindex=ReindexStrategy(blockwise=True))
     return final[agg.name], (final["groups"],)

@@ -66,8 +66,9 @@ def reindex_(array, from_, to, *, array_type: ReindexArrayType = ReindexArrayTyp
         if torchy:
             return torch.full(shape, fill_value, dtype=array.dtype, device=array.device)
         return np.full(shape, fill_value, dtype=array.dtype)
-    from_ = pd.Index(from_.cpu().numpy() if is_torch(from_) else from_)
-    if from_.equals(to) and array_type.is_same_type(array):
+    if not isinstance(from_, pd.Index):
+        from_ = pd.Index(from_.cpu().numpy() if is_torch(from_) else from_)
+    if from_.equals(to) and array_type.is_same_type(array):  # O(1) for two RangeIndex objects
         return array
     if from_.dtype.kind == "O" and isinstance(from_[0], tuple):
         raise NotImplementedError("Currently does not support reindexing with object arrays of tuples.")
