@@ -285,13 +285,24 @@ k_rows_bins(const VT* __restrict__ vals, const long long* __restrict__ perm, con
     }
     __syncwarp();
     int64_t k = lane;
-    // 8 independent coalesced loads in flight per lane (4 left the SM at ~16 KB in flight: 40% of the HBM roof)
-    for (; k + 224 < n; k += 256) {
-      VT x[8];
+    // 16 independent coalesced loads in flight per lane: 4 left the SM at ~16 KB in flight and 40% of the HBM roof
+    constexpr int U = 16;
+    for (; k + 32 * (U - 1) < n; k += 32 * U) {
+      VT x[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] = __ldg(row + k + 32 * u);
+      for (int u = 0; u < U; ++u) x[u] = __ldg(row + k + 32 * u);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < U; ++u) {
+        const int s = (int)code[k + 32 * u] * 32 + lane;
+        if (is_nan(x[u])) nans[s]++; else bins[s] = CA::step(bins[s], x[u]);
+      }
+    }
+    for (; k + 96 < n; k += 128) {
+      VT x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = __ldg(row + k + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
         const int s = (int)code[k + 32 * u] * 32 + lane;
         if (is_nan(x[u])) nans[s]++; else bins[s] = CA::step(bins[s], x[u]);
       }

@@ -143,7 +143,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
 // > 0 iff the group has NaNs, which is all floxb_finalize consults).
 // The tile loop is software-pipelined (loads of tile t+1 in flight during the atomics of tile t) and walks
 // the chunk table monotonically (no per-tile binary search): tools/kbench.py v22 vs v9.
-constexpr int kSweepTiles = 64;  // tiles of THREADS*4 rows: ~26 adds per slot between sweeps at G = 1e4
+constexpr int kSweepTiles = 64;  // upper bound, tiles of THREADS*4 rows: ~26 adds per slot between sweeps at G = 1e4
 constexpr unsigned kDrainEvery = 32;  // <= this many (+ racing) addends per f32 partial, whatever the skew
 
 // WS: level 2 lives in a caller-provided, CTA-private slice of GLOBAL memory (L2-resident: 148 x G x 8 B)
@@ -203,9 +203,12 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int G, double* __rest
   // tiles.  A row racing with the sweep either lands before the exchange (moved now) or in the fresh zero
   // (moved by the next sweep); its count may travel one sweep later than its value, which only matters to the
   // drain heuristic.  (tools/kbench3.py: __syncthreads-fenced sweeps cost 7 points of roofline, these 2.)
+  // sweep interval: ~24 adds per slot between sweeps for evenly spread groups (64 tiles at S = 1e4; fewer for the
+  // replicated small-G layouts, whose slots would otherwise fill up and take the drain path every 32 adds)
+  const int sweep_tiles = max(4, min(kSweepTiles, (int)(((int64_t)S * 24) / (THREADS * 4))));
   int since_sweep = 0;
   walk_tiles<float, CT, THREADS>(tab, add_row, [&] {
-    if (++since_sweep == kSweepTiles) {
+    if (++since_sweep == sweep_tiles) {
       since_sweep = 0;
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {
         const unsigned c = atomicExch(&scnt[sl], 0u);
