@@ -370,7 +370,7 @@ def run_gpu(args):
     peak, peak_src = hbm_peak()
     achieved = BYTES_PER_ROW * launch_rows / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_moments_smem_f32<long,SUM,1024,1,0,WS> (floxb_moments, two-level f32 bins)",
+                "traffic": ncu_traffic(), "kernel": "k_moments_smem_f32<long,SUM,1024,0,WS> (floxb_moments, two-level f32 bins)",
                 "peak_source": peak_src, "kernel_ms_per_launch": kernel_ms, "rows_per_launch": launch_rows,
                 "launches_per_step": -(-len(arr.chunks) // per_launch), "algorithmic_bytes_per_launch": BYTES_PER_ROW * launch_rows,
                 "secondary_limit": "L1TEX shared-memory wavefronts (atomic CAS on privatised bins), see profiles/"}

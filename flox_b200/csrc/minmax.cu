@@ -15,7 +15,7 @@ template <typename K, bool IS_MAX> __device__ __forceinline__ void key_update(K*
 
 // RSHIFT: 2^RSHIFT slot copies per group selected by the low lane bits (see k_moments_smem): with 32 copies the
 // lanes of a warp never collide on an address or a bank, which matters for small G.
-template <typename VT, typename CT, bool IS_MAX, int THREADS, int ITERS, int RSHIFT>
+template <typename VT, typename CT, bool IS_MAX, int THREADS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_minmax_smem(const __grid_constant__ ChunkTable tab, int G, long long* __restrict__ gkey,
               unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan) {
@@ -98,7 +98,6 @@ __global__ void k_fill_key(long long* key, unsigned long long* cnt, unsigned lon
 }
 
 constexpr int kMMThreads = 1024;
-constexpr int kMMIters = 1;
 constexpr size_t kMMSmemBudget = 227 * 1024;
 
 template <typename VT, typename CT, bool IS_MAX>
@@ -119,12 +118,12 @@ int launch_minmax(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
   if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
   if (use_smem) {
-    constexpr int TILE = kMMThreads * 4 * kMMIters;
+    constexpr int TILE = kMMThreads * 4;
     using KernT = void (*)(const ChunkTable, int, long long*, unsigned long long*, unsigned long long*);
-    KernT kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 0>;
+    KernT kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, 0>;
     size_t smem_used = smem;
-    if (smem * 32 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 5>; smem_used = smem * 32; }
-    else if (smem * 8 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, kMMIters, 3>; smem_used = smem * 8; }
+    if (smem * 32 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, 5>; smem_used = smem * 32; }
+    else if (smem * 8 <= kMMSmemBudget) { kern = k_minmax_smem<VT, CT, IS_MAX, kMMThreads, 3>; smem_used = smem * 8; }
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMMSmemBudget) != cudaSuccess)
       return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {

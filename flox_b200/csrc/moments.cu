@@ -52,7 +52,7 @@ template <typename VT, int OP> struct Slot {
 // lanes of a warp never share a slot and slot (c*32 + lane) sits in bank `lane`: no CAS retries and
 // no bank conflicts for small G (at G = 100 the un-replicated CAS loop is 2.6x slower than at
 // G = 1e4).  The launcher picks the largest replication that fits shared memory.
-template <typename VT, typename CT, int OP, int THREADS, int ITERS, int RSHIFT>
+template <typename VT, typename CT, int OP, int THREADS, int RSHIFT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
                typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
@@ -151,7 +151,7 @@ constexpr unsigned kDrainEvery = 32;  // <= this many (+ racing) addends per f32
 // hot-slot drains, and it shrinks the kernel's shared-memory footprint from 16 to 8 bytes per slot — which
 // matters because the L1 that backs the streaming loads is whatever shared memory leaves over
 // (tools/kbench.py: the same loop runs 26% slower with 200 KB than with 120 KB of dynamic shared memory).
-template <typename CT, int OP, int THREADS, int ITERS, int RSHIFT, bool WS>
+template <typename CT, int OP, int THREADS, int RSHIFT, bool WS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int G, double* __restrict__ gacc,
                    unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan,
@@ -375,7 +375,6 @@ __global__ void k_fill_acc(AccT* acc, unsigned long long* cnt, unsigned long lon
 // host-side launchers
 // ------------------------------------------------------------------------------------------
 constexpr int kSmemThreads = 1024;
-constexpr int kSmemIters = 1;  // tiles of THREADS*4 rows, double-buffered by walk_tiles
 constexpr size_t kSmemBudget = 227 * 1024;
 
 template <typename VT, int OP> size_t smem_bytes_moments(int64_t G) {
@@ -404,8 +403,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   if (force_path == 2) use_smem = false;
 
   if (use_smem) {
-    constexpr int kIters = kSmemIters;
-    constexpr int TILE = kSmemThreads * 4 * kIters;
+    constexpr int TILE = kSmemThreads * 4;
     using KernT = void (*)(const ChunkTable, int, AccT*, unsigned long long*, unsigned long long*);
     using KernWsT = void (*)(const ChunkTable, int, double*, unsigned long long*, unsigned long long*, double*);
     KernT kern = nullptr;
@@ -413,14 +411,14 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
       auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
-      if (bytes(32) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 5, false>; smem_used = bytes(32); }
-      else if (bytes(8) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 3, false>; smem_used = bytes(8); }
-      else if (use_ws) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, true>; }
-      else { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, kIters, 0, false>; }
+      if (bytes(32) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 5, false>; smem_used = bytes(32); }
+      else if (bytes(8) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 3, false>; smem_used = bytes(8); }
+      else if (use_ws) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, true>; }
+      else { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, false>; }
     } else {
-      kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 0>;
-      if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 5>; smem_used = smem * 32; }
-      else if (smem * 8 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, kSmemIters, 3>; smem_used = smem * 8; }
+      kern = k_moments_smem<VT, CT, OP, kSmemThreads, 0>;
+      if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, 5>; smem_used = smem * 32; }
+      else if (smem * 8 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, 3>; smem_used = smem * 8; }
     }
     if (cudaFuncSetAttribute(kern_ws ? (const void*)kern_ws : (const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)kSmemBudget) != cudaSuccess)

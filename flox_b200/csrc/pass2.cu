@@ -30,7 +30,7 @@ __global__ void k_group_means(const typename Acc<VT>::type* __restrict__ acc, co
 }
 
 // ---- squared deviations -----------------------------------------------------------------
-template <typename VT, typename CT, int THREADS, int ITERS>
+template <typename VT, typename CT, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 k_sqdev_smem(const __grid_constant__ ChunkTable tab, int G, const double* __restrict__ means,
              int skipna, double* __restrict__ gm2) {
@@ -150,7 +150,6 @@ static inline dim3 generic_grid(int64_t row_len, int64_t A) {
 static inline int fill_blocks(int64_t n) { return (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184); }
 
 constexpr int kSqThreads = 1024;
-constexpr int kSqIters = 1;
 
 template <typename VT, typename CT>
 int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, const double* means,
@@ -160,8 +159,8 @@ int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64
   if (nbins == 0) return FLOXB_OK;
   const size_t smem = (size_t)G * ((sizeof(VT) == 4 && is_float<VT>::value) ? 12 : 16);
   if (A == 1 && B == 1 && smem <= 227 * 1024) {
-    constexpr int TILE = kSqThreads * 4 * kSqIters;
-    auto kern = k_sqdev_smem<VT, CT, kSqThreads, kSqIters>;
+    constexpr int TILE = kSqThreads * 4;
+    auto kern = k_sqdev_smem<VT, CT, kSqThreads>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return FLOXB_ECUDA;
     for (int64_t c0 = 0; c0 < n_chunks; c0 += kMaxChunksPerLaunch) {
       ChunkTable tab;
