@@ -26,6 +26,12 @@ ncukexp)
       python tools/kbench.py 268435456 > gpurun_out/ncu_kexp.log 2>&1 ;;
 kbench3)
   timeout 600 python tools/kbench3.py > gpurun_out/kbench3.log 2>&1 ;;
+ncusecond)
+  for pair in rows:k_rows_bins c5:k_moments_global_runs c3:k_cols; do
+    cfg=${pair%%:*}; kern=${pair##*:}
+    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$kern -c 2 -f -o gpurun_out/prof_$kern \
+        python tools/configs_bench.py $cfg > gpurun_out/ncu_$kern.log 2>&1
+  done ;;
 ncuother)
   timeout 1200 ncu --set full --clock-control none --import-source on -k 'regex:k_moments_global|k_rows|k_sqdev_global' -c 8 -f -o gpurun_out/prof_other \
       python tools/configs_bench.py c4 c5 rows > gpurun_out/ncu_other.log 2>&1 ;;
