@@ -269,13 +269,14 @@ def test_time_major_layout_column_kernels(dtype):
         assert_same(got_t.cpu().numpy(), want, what=f"cols-torch/{func}/{np.dtype(dtype)}", **_tols(func, base))
 
 
-@pytest.mark.parametrize("ngroups", [13, 40])
+@pytest.mark.parametrize("ngroups,T", [(13, 3650), (13, 3651), (40, 3650)])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
-def test_row_batched_layout_warp_per_row_kernels(dtype, ngroups):
+def test_row_batched_layout_warp_per_row_kernels(dtype, ngroups, T):
     """(lat*lon, time) rows sharing one label vector — the layout flox's own reshape produces.  13 groups take the
-    lane-private-bin kernel (k_rows_bins, G <= 32), 40 groups the permutation kernel (k_rows)."""
+    lane-private-bin kernel (k_rows_bins, G <= 32: pair loads for even T, scalar loads for odd T), 40 groups the
+    permutation kernel (k_rows)."""
     rng = np.random.default_rng(21)
-    A, T = 700, 3650
+    A = 700
     arr = (rng.random((A, T)) * 10 - 2).astype(dtype)
     if np.dtype(dtype).kind == "f":
         arr[5, rng.random(T) < 0.1] = np.nan
