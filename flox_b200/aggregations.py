@@ -224,7 +224,13 @@ def _initialize_aggregation(func, dtype, array_dtype, fill_value, min_count: int
     elif isinstance(func, str):
         if func not in AGGREGATIONS:
             raise NotImplementedError(f"Reduction {func!r} not implemented yet")
-        agg = copy.deepcopy(AGGREGATIONS[func])
+        # prototypes hold only immutable tuples / callables besides these dicts: a shallow clone is enough and
+        # saves the ~50-object deepcopy on every call
+        proto = AGGREGATIONS[func]
+        agg = copy.copy(proto)
+        agg.fill_value = dict(proto.fill_value)
+        agg.finalize_kwargs = dict(proto.finalize_kwargs) if getattr(proto, "finalize_kwargs", None) else {}
+        agg.dtype = None
     else:
         raise ValueError("Bad type for func. Expected str or Aggregation")
 
