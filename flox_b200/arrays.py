@@ -1,10 +1,16 @@
 """Container plumbing: numpy / torch in, torch-on-device inside, same kind out."""
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 
 from .kernels import default_device
+
+# read-only inputs (broadcast views, arrays handed over by xarray) are only ever READ here; torch.from_numpy warns
+# about them once per process
+warnings.filterwarnings("ignore", message="The given NumPy array is not writable", category=UserWarning)
 
 _NP2TORCH = {
     np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64, np.dtype("float16"): torch.float16,
