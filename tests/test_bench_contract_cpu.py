@@ -1,0 +1,46 @@
+"""bench.py's reference arm (`--impl reference`, the oracle port on the host cores) runs without a GPU and prints
+ONE JSON line with the keys the driver reads; its own arm must refuse to run without CUDA instead of timing a
+fallback."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT,
+                          env=e, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    p = _run("--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "0", "--rows", "400000", "--chunk", "50000")
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    row = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in row, key
+    assert row["impl"] == "reference" and row["unit"] == "rows/s" and row["value"] > 0
+    assert row["cpu_baseline"]["kind"] == "port" and row["cpu_baseline"]["cores"] >= 1
+    assert row["e2e"]["h2d_bytes_per_step"] == 0 and row["e2e"]["value"] == row["value"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    p = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--rows", "400000", "--chunk", "50000",
+             env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert p.returncode == 0 and not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine WITHOUT a GPU")
+def test_own_arm_refuses_to_run_without_cuda():
+    p = _run("--gpus", "1", "--steps", "1", "--warmup", "0", "--rows", "400000", "--chunk", "50000")
+    assert p.returncode != 0
+    assert not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
