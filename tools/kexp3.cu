@@ -8,7 +8,7 @@ using namespace floxb;
 
 namespace {
 
-enum : unsigned { F_WALK = 1, F_NAN = 2, F_RET = 4, F_SWEEP = 8, F_WS = 16, F_NOPF = 32, F_PF8 = 64, F_WALK2 = 128, F_SWEEP2 = 256, F_SW64 = 512 };
+enum : unsigned { F_WALK = 1, F_NAN = 2, F_RET = 4, F_SWEEP = 8, F_WS = 16, F_NOPF = 32, F_PF8 = 64, F_WALK2 = 128, F_SWEEP2 = 256, F_SW64 = 512, F_PACKED = 1024 };
 
 template <unsigned F>
 __global__ void __launch_bounds__(1024, 1)
@@ -50,6 +50,12 @@ k_bisect(const __grid_constant__ ChunkTable tab, const float* __restrict__ vals,
       }
     }
     const int sl = (int)c;
+    if constexpr ((F & F_PACKED) != 0) {
+      // upper bound of a "count and fixed-point sum in ONE native 32-bit ATOMS.ADD" design: [count 6 bits | sum 26 bits].
+      // Throughput probe only (no drains, the fields overflow): what would removing the LDS + CAS loop buy?
+      atomicAdd(&scnt[sl], (1u << 26) + (unsigned)__float2int_rn(v * 524288.0f));
+      return;
+    }
     atomicAdd(&spart[sl], v);
     if constexpr ((F & F_RET) != 0) {
       const unsigned seen = atomicAdd(&scnt[sl], 1u);
@@ -176,6 +182,8 @@ extern "C" int kexp3_run(int variant, const float* v, const long long* c, int64_
     V(17, F_NAN | F_RET | F_SWEEP2 | F_WS)
     V(18, F_WALK2 | F_NAN | F_RET | F_SWEEP2 | F_WS | F_SW64)
     V(19, F_WALK2 | F_NAN | F_RET | F_SWEEP | F_WS | F_SW64)
+    V(20, F_PACKED)
+    V(21, F_WALK2 | F_NAN | F_PACKED)
   }
   return -1;
 }
@@ -185,6 +193,7 @@ extern "C" const char* kexp3_name(int variant) {
                                 "bare+nan+ret+sweep(ws)", "walk, no L2 prefetch", "bare+nan+ret", "walk, L2 prefetch 8 ahead",
                                 "bare+sweep(ws)", "bare+nan", "bare+ret", "walk2", "walk2+nan+ret", "walk2+nan+ret+sweep(ws)",
                                 "walk2+nan+ret+sweep2(ws, no barrier)", "bare+nan+ret+sweep2", "walk2+nan+ret+sweep2 every 64",
-                                "walk2+nan+ret+sweep(ws) every 64"};
-  return (variant >= 0 && variant < 20) ? names[variant] : "?";
+                                "walk2+nan+ret+sweep(ws) every 64", "bare, ONE native atomic per row (packed probe)",
+                                "walk+nan, ONE native atomic per row (packed probe)"};
+  return (variant >= 0 && variant < 22) ? names[variant] : "?";
 }
