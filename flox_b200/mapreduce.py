@@ -134,7 +134,10 @@ def _stage_packed_codes(label_chunks: dict, n_groups: int, device, world: int) -
         return {}
     sdt = torch.int16 if n_groups <= 32767 else torch.int32
     kern, pool = get_kernels(), _pool(world)
-    staged = {k: torch.empty(h.size, dtype=sdt, pin_memory=True) for k, h in todo.items()}
+    try:
+        staged = {k: torch.empty(h.size, dtype=sdt, pin_memory=True) for k, h in todo.items()}
+    except RuntimeError:  # no pinned memory left for the staging buffers: copy the labels as they are
+        return {}
     futures = {k: pool.submit(kern.host_pack_codes, h, n_groups, staged[k]) for k, h in todo.items()}
     out = {}
     for k in todo:
