@@ -103,8 +103,9 @@ _last_encoder: tuple = (None, None, None)
 
 def int_label_encoder(expect: pd.Index, sort: bool) -> IntLabelEncoder:
     global _last_encoder
-    if _last_encoder[0] is expect and _last_encoder[1] == sort:
-        return _last_encoder[2]
+    cached = _last_encoder  # ONE read: other threads replace the tuple as a whole (dask's threaded scheduler)
+    if cached[0] is expect and cached[1] == sort:
+        return cached[2]
     enc = IntLabelEncoder(expect, sort)
     _last_encoder = (expect, sort, enc)
     return enc

@@ -106,3 +106,37 @@ def test_unknown_integer_labels_are_discovered_without_a_host_hash(label_dtype, 
         want, want_groups = O.groupby_reduce(x, wide, func="sum")
         assert np.array_equal(groups, np.asarray(want_groups))
         assert_same(got, want, what="discover/wide", rtol_f32=RTOL32, rtol_f64=RTOL64)
+
+
+def test_concurrent_calls_from_many_threads(emu):  # noqa: F811
+    """dask's threaded scheduler calls chunk_reduce from many threads at once (reference tests/test_core.py:1827-1851):
+    the host logic keeps no per-call state in module globals (the encoder cache and the transfer counters are the only
+    shared objects, both benign), so concurrent calls with different arguments must not disturb each other."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import flox_oracle as O
+
+    rng = np.random.default_rng(3)
+    jobs = []
+    for i in range(24):
+        n, g = int(rng.integers(50, 400)), int(rng.integers(2, 9))
+        x = (rng.random((2, n)) * 6 - 2).astype(np.float32 if i % 2 else np.float64)
+        x[:, rng.random(n) < 0.1] = np.nan
+        by = rng.integers(0, g, n) * (i % 3 + 1)          # different label sets: different encoders per call
+        func = ["nansum", "nanmean", "max", "count", "nanvar", "sum"][i % 6]
+        eg = None if i % 4 == 0 else np.unique(by)
+        jobs.append((x, by, func, eg))
+
+    def run(job):
+        x, by, func, eg = job
+        return flox_b200.groupby_reduce(x, by, func=func, expected_groups=eg)
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        for _ in range(3):
+            results = list(ex.map(run, jobs))
+            for (x, by, func, eg), (got, groups) in zip(jobs, results):
+                want, want_groups = O.groupby_reduce(x, by, func=func, expected_groups=eg)
+                np.testing.assert_array_equal(np.asarray(groups), np.asarray(want_groups))
+                r64 = RTOL32 if x.dtype == np.float32 else RTOL64
+                assert_same(got, want, what=f"threads/{func}", rtol_f32=RTOL32, rtol_f64=r64,
+                            atol_f32=cond_atol(func, x, RTOL32), atol_f64=cond_atol(func, x, r64))
