@@ -104,9 +104,9 @@ class ChunkedArray:
         for b in bys:
             if is_chunked(b):
                 per_by_chunks.append(b.rechunk_like(template).chunks)
-            else:
-                cb = ChunkedArray.from_array(b, 1).rechunk_like(template) if b.shape[-1] != 0 else None
-                per_by_chunks.append(cb.chunks)
+            else:  # in-memory labels next to chunked ones: slice them by the template's chunk boundaries
+                bounds = np.concatenate([[0], np.cumsum(template.chunk_sizes)])
+                per_by_chunks.append([b[..., int(lo):int(hi)] for lo, hi in zip(bounds[:-1], bounds[1:])])
         out_chunks, found, grp_shape = [], None, None
         for parts in zip(*per_by_chunks):
             (codes,), found, grp_shape = _factorize_multiple(tuple(parts), expected_groups, sort=sort)

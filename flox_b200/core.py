@@ -440,7 +440,10 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
     if not any(isbins):
         eg = list(expected_groups)
         for i, ex in enumerate(eg):
-            if isinstance(ex, np.ndarray) and ex.ndim == 1 and ex.dtype.kind in "iu" and ex.size > 0 and _is_arange(ex):
+            # only for INTEGER labels: float labels with fractional values must be dropped by the
+            # searchsorted + isin lookup (factorize.py:84-94), not truncated into a neighbouring group
+            if (isinstance(ex, np.ndarray) and ex.ndim == 1 and ex.dtype.kind in "iu" and ex.size > 0
+                    and np_dtype_of(bys[i]).kind in "iu" and _is_arange(ex)):
                 arange_like[i] = ex.dtype
                 eg[i] = pd.RangeIndex(ex.size)
         expected_groups = tuple(eg)
@@ -471,6 +474,12 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
     if is_npdatetime and func != "count":
         array = array.view(np.int64)
         array_dtype = np.dtype(np.int64)
+    elif is_npdatetime and isinstance(array, np.ndarray):
+        # count of datetimes = number of non-NaT values: hand the kernels a float array that is NaN exactly where the
+        # input is NaT.  timedelta64 is an np.integer subclass, which the reference's notnull() treats as "cannot
+        # be missing" (xrutils.py:149-160): every timedelta, NaT included, counts — reproduced as is.
+        array = np.where(np.isnat(array), np.nan, 0.0) if array.dtype.kind == "M" else np.zeros(array.shape)
+        array_dtype = np.dtype(np.float64)
 
     assert nax <= by_.ndim
     if nax < by_.ndim:

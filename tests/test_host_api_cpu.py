@@ -140,3 +140,51 @@ def test_concurrent_calls_from_many_threads(emu):  # noqa: F811
                 r64 = RTOL32 if x.dtype == np.float32 else RTOL64
                 assert_same(got, want, what=f"threads/{func}", rtol_f32=RTOL32, rtol_f64=r64,
                             atol_f32=cond_atol(func, x, RTOL32), atol_f64=cond_atol(func, x, r64))
+
+
+# ---- advisor findings (round 1): values below are the reference's own answers ----------------------
+def _reference_or_none():
+    from oracle import ref_loader
+
+    return ref_loader.load_reference() if ref_loader.reference_available() else None
+
+
+@pytest.mark.parametrize("func,want", [("sum", [16.0, 2.0, 4.0]), ("count", [1, 1, 1]), ("max", [16.0, 2.0, 4.0])])
+def test_fractional_float_labels_are_dropped_not_truncated(func, want, emu):  # noqa: F811
+    """float `by` + integer 0..G-1 expected_groups: 0.5 / 1.5 belong to NO group (factorize.py:84-94)."""
+    x = np.array([1.0, 2, 4, 8, 16])
+    by = np.array([0.5, 1, 2, 1.5, 0])
+    got, groups = flox_b200.groupby_reduce(x, by, func=func, expected_groups=np.array([0, 1, 2]))
+    np.testing.assert_array_equal(got, np.asarray(want))
+    np.testing.assert_array_equal(groups, [0, 1, 2])
+    ref = _reference_or_none()
+    if ref is not None:
+        rwant, _ = ref.groupby_reduce(x, by, func=func, expected_groups=np.array([0, 1, 2]), engine="flox")
+        np.testing.assert_array_equal(got, rwant)
+
+
+@pytest.mark.parametrize("kind", ["M8[ns]", "m8[ns]"])
+def test_count_of_datetimes_excludes_nat(kind, emu):  # noqa: F811
+    d = np.array([1, np.iinfo(np.int64).min, 3, 4], dtype=np.int64).view(kind)  # INT64_MIN is NaT
+    by = np.array([0, 0, 1, 1])
+    got, _ = flox_b200.groupby_reduce(d, by, func="count")
+    assert got.dtype == np.dtype(np.intp)
+    # timedelta64 subclasses np.integer: the reference's notnull() counts its NaT as valid (xrutils.py:149-160)
+    np.testing.assert_array_equal(got, [1, 2] if kind[0] == "M" else [2, 2])
+    ref = _reference_or_none()
+    if ref is not None:
+        rwant, _ = ref.groupby_reduce(d, by, func="count", engine="flox")
+        np.testing.assert_array_equal(got, rwant)
+        assert got.dtype == rwant.dtype
+
+
+def test_in_memory_labels_next_to_chunked_ones(emu):  # noqa: F811
+    """a plain `by` mixed with a chunked one is sliced by chunk boundaries (no per-element objects)."""
+    rng = np.random.default_rng(3)
+    x = rng.random(1000)
+    b0, b1 = rng.integers(0, 3, 1000), rng.integers(0, 4, 1000)
+    xa = flox_b200.ChunkedArray.from_array(x, 300)
+    got, *_ = flox_b200.groupby_reduce(xa, flox_b200.ChunkedArray.from_array(b0, 300), b1, func="sum",
+                                       expected_groups=(np.arange(3), np.arange(4)), method="map-reduce")
+    want, *_ = flox_b200.groupby_reduce(x, b0, b1, func="sum", expected_groups=(np.arange(3), np.arange(4)))
+    np.testing.assert_allclose(np.asarray(got), np.nan_to_num(want), rtol=1e-12)
