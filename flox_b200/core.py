@@ -57,6 +57,10 @@ def _transpose(x, order):
 
 
 def _broadcast_to(x, shape):
+    if tuple(x.shape) == tuple(shape):
+        return x
+    if not (is_torch(x) or isinstance(x, np.ndarray)):
+        raise NotImplementedError("chunked labels must already have the broadcast shape of all `by`")
     return x.broadcast_to(shape) if is_torch(x) else np.broadcast_to(x, shape)
 
 
