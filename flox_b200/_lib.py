@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libflox_b200.so")
 
 F32, F64, I32, I64 = 0, 1, 2, 3
 OP_SUM, OP_PROD, OP_SUMSQ = 0, 1, 2
-FIN_SUM, FIN_NANLEN, FIN_MEAN, FIN_MAX, FIN_MIN, FIN_VAR, FIN_STD, FIN_ARG, FIN_COUNT_ALL = range(9)
+FIN_SUM, FIN_NANLEN, FIN_MEAN, FIN_MAX, FIN_MIN, FIN_VAR, FIN_STD, FIN_ARG = range(8)
 COMB_SUM, COMB_MAX, COMB_MIN, COMB_PROD, COMB_NANMAX, COMB_NANMIN = range(6)
 
 

@@ -41,7 +41,6 @@ k_finalize(int kind, const void* __restrict__ acc_, const void* __restrict__ acc
         break;
       }
       case FLOXB_FIN_NANLEN: r = rows == 0 ? fill : (OT)c; break;
-      case FLOXB_FIN_COUNT_ALL: r = (OT)rows; break;
       case FLOXB_FIN_MEAN: {
         const AccT a = reinterpret_cast<const AccT*>(acc_)[i];
         double s;
@@ -220,7 +219,7 @@ extern "C" int floxb_finalize(int kind, int value_dtype, int out_dtype, const vo
   if (n_bins < 0) return FLOXB_EINVAL;
   if (n_bins == 0) return FLOXB_OK;
   if (!out || !cnt) return FLOXB_EINVAL;
-  if (kind != FLOXB_FIN_NANLEN && kind != FLOXB_FIN_COUNT_ALL && !acc) return FLOXB_EINVAL;
+  if (kind != FLOXB_FIN_NANLEN && !acc) return FLOXB_EINVAL;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (value_dtype) {
     case FLOXB_F32: return finalize_out<float>(out_dtype, kind, acc, acc2, cnt, nnan, n_bins, skipna, fill_f, fill_i, min_count, mc_fill_f, mc_fill_i, ddof, out, group_major_ab, st);

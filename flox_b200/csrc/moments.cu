@@ -38,12 +38,6 @@ template <typename VT, int OP> __device__ __forceinline__ typename Acc<VT>::type
   else return w;
 }
 
-// Shared-memory slot type per (value type, op): f32 partials for f32 sums / sums of squares.
-constexpr unsigned kFlushEvery = 8;  // power of two
-template <typename VT, int OP> struct Slot {
-  using type = typename Acc<VT>::type;
-  static constexpr bool partial = false;
-};
 
 // ------------------------------------------------------------------------------------------
 // shared-memory privatised bins
@@ -59,8 +53,7 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
                unsigned long long* __restrict__ gnan) {
   using AccT = typename Acc<VT>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using ST = typename Slot<VT, OP>::type;
-  constexpr bool kPartial = Slot<VT, OP>::partial;
+  using ST = AccT;  // one exact 64-bit slot (f64 / i64) per group copy
   constexpr int R = 1 << RSHIFT;
   const int S = G << RSHIFT;  // slots
   ST* sacc = reinterpret_cast<ST*>(smem_raw);
@@ -81,16 +74,6 @@ k_moments_smem(const __grid_constant__ ChunkTable tab, int G,
       const int s = ((int)c << RSHIFT) | copy;
       if (is_nan(v)) {
         if constexpr (is_float<VT>::value) atomicAdd(&snan[s], 1u);
-      } else if constexpr (kPartial) {
-        const float w = (OP == FLOXB_OP_SUMSQ) ? v * v : v;
-        atomicAdd(&sacc[s], w);
-        const unsigned seen = atomicAdd(&scnt[s], 1u);
-        if ((seen & (kFlushEvery - 1)) == kFlushEvery - 1) {
-          // drain this slot's f32 partial into the f64 accumulator; atomicExch hands the partial to
-          // exactly one thread, concurrent adds land in the fresh zero
-          const float part = atomicExch(&sacc[s], 0.0f);
-          atomic_add(&gacc[(int)c], (AccT)part);
-        }
       } else {
         acc_apply_shared<AccT, OP>(&sacc[s], lift<VT, OP>(v));
         atomicAdd(&scnt[s], 1u);
@@ -243,6 +226,167 @@ k_moments_smem_f32(const __grid_constant__ ChunkTable tab, int G, double* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// fixed-point level 1 for f32 sums: TWO NATIVE integer atomics per row, no CAS loop
+// ------------------------------------------------------------------------------------------
+// The two-level kernel above is bound by shared-memory wavefronts, not by HBM: an f32 add to shared memory is an
+// LDS + ATOMS.CAST.SPIN loop (a CAS costs two wavefronts per conflict way) next to the native counter add
+// (profiles/r01_ncu_moments_twolevel_leanwalk_summary.json: 16.3 wavefronts per 32 rows, L1TEX 96% busy).  The only
+// native shared-memory add on sm_100a is the 32-bit integer ATOMS.ADD, so this kernel makes level 1 an INTEGER:
+//
+//   slot = { lo : u32,  hi : u32 = [count:13 | sum bits 32..50:19] }        (8 bytes per slot, as before)
+//
+// A row adds the 64-bit fixed-point number  a' = 2^37 +- m * 2^sh  (m = the 24-bit significand, sh = the row's
+// exponent relative to a per-CTA base e_lo, 0 <= sh <= 13; the 2^37 bias keeps every addend non-negative and is
+// removed again through the count) with
+//      old = ATOMS.ADD(lo, a'_lo);   ATOMS.ADD(hi, 2^19 + a'_hi + carry(old, a'_lo))
+// Both are native and RETURNING: the first return value yields the carry, the second the slot's add count, which
+// triggers the hot-slot drain.  Every row contributes its full amount to whichever sweep picks up each half, and a
+// carry is produced by exactly the add that wrapped `lo`, so the 64-bit total is exact under any interleaving of
+// adds, sweeps and drains (a wrap and its carry may land in different sweeps: the two swept values are then off by
+// -+2^32 units and cancel in level 2).  The conversion is EXACT or not taken: a value whose bits do not fit the
+// window (|v| >= 2^(e_lo+14-127), or low significand bits below 2^(e_lo-150) set; infinities) is added to the
+// global f64 accumulator directly.  e_lo comes from the largest exponent in a 1024-value sample of the launch's data
+// (+1 binade of headroom), so for data within ~4 decades of its maximum (uniform, normal, physical fields) almost
+// every row takes the two-atomic path: 2 x ~3.5 conflict wavefronts per 32 rows instead of 16.
+// Field budget: 24 (significand) + 1 (bias) + 13 (window) + 13 (adds) = 51 sum bits; a slot is drained when its count
+// reaches kFxDrain and at most THREADS*4 more adds can be in flight, so count <= 1024 + 4096 < 2^13.
+// Level 2, sweeps, NaN flags and the final merge are those of k_moments_smem_f32; sums are exact integers until they are
+// rounded ONCE per sweep into the f64 level 2 (|value| < 2^51: exact conversion).
+constexpr int kFxWindow = 13;                       // accepted shifts 0..13
+constexpr unsigned long long kFxBias = 1ull << (24 + kFxWindow);
+constexpr int kFxCountShift = 19;                   // hi = [count:13 | sum:19]
+constexpr unsigned kFxDrain = 1024;
+
+__device__ __forceinline__ long long fx_value(unsigned h, unsigned l) {
+  return (long long)(((unsigned long long)(h & ((1u << kFxCountShift) - 1u)) << 32) | (unsigned long long)l) -
+         (long long)(h >> kFxCountShift) * (long long)kFxBias;
+}
+
+template <typename CT, int THREADS, int RSHIFT, bool WS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_moments_smem_fx(const __grid_constant__ ChunkTable tab, int G, double* __restrict__ gacc,
+                  unsigned long long* __restrict__ gcnt, unsigned long long* __restrict__ gnan,
+                  double* __restrict__ workspace) {
+  constexpr int R = 1 << RSHIFT;
+  const int S = G << RSHIFT;
+  const int NW = (G + 31) >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const size_t ws_stride = (size_t)S * 8 + (((size_t)S * 4 + 7) & ~(size_t)7);
+  double* sacc = WS ? reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)blockIdx.x * ws_stride)
+                    : reinterpret_cast<double*>(smem_raw);
+  unsigned* stot = WS ? reinterpret_cast<unsigned*>(sacc + S) : reinterpret_cast<unsigned*>(smem_raw + (size_t)S * 8);
+  unsigned* slo = reinterpret_cast<unsigned*>(smem_raw + (WS ? 0 : (size_t)S * 12));  // [S]
+  unsigned* shi = slo + S;                                                             // [S]
+  unsigned* snanbits = shi + S;                                                        // [NW]
+  __shared__ int s_emax;
+  const int copy = threadIdx.x & (R - 1);
+  if (threadIdx.x == 0) s_emax = 0;
+  for (int s = threadIdx.x; s < S; s += THREADS) {
+    sacc[s] = 0.0;
+    stot[s] = 0u;
+    slo[s] = 0u;
+    shi[s] = 0u;
+  }
+  for (int w = threadIdx.x; w < NW; w += THREADS) snanbits[w] = 0u;
+  __syncthreads();
+  {  // exponent base: the largest finite exponent among THREADS values sampled across the launch's chunks
+    int e = 0;
+    const unsigned h = ((unsigned)blockIdx.x * THREADS + threadIdx.x) * 2654435761u;
+    int k = (int)(h % (unsigned)tab.nchunks);
+    for (int t = 0; t < 4 && tab.n[k] == 0; ++t) k = (k + 1) % tab.nchunks;
+    if (tab.n[k] > 0) {
+      const unsigned long long r = ((unsigned long long)h * 0x9E3779B97F4A7C15ull) >> 20;
+      const unsigned b = __float_as_uint(reinterpret_cast<const float*>(tab.values[k])[r % (unsigned long long)tab.n[k]]);
+      e = (int)((b >> 23) & 0xffu);
+      if (e == 0xff) e = 0;
+    }
+    e = __reduce_max_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0 && e > 0) atomicMax(&s_emax, e);
+  }
+  __syncthreads();
+  const int e_lo = max(1, min(s_emax + 1, 254) - kFxWindow);
+  const double scale = __longlong_as_double((long long)(e_lo - 150 + 1023) << 52);  // 2^(e_lo - 150)
+
+  auto to_level2 = [&](int sl, unsigned h, unsigned l) {
+    atomicAdd(&sacc[sl], (double)fx_value(h, l) * scale);
+    atomicAdd(&stot[sl], h >> kFxCountShift);
+  };
+  auto add_row = [&](float v, CT c) {
+    if ((unsigned long long)c >= (unsigned long long)G) return;
+    const unsigned bits = __float_as_uint(v);
+    const unsigned e = (bits >> 23) & 0xffu;
+    const unsigned m = (bits & 0x7fffffu) | (e ? 0x800000u : 0u);
+    const int sh = (int)(e ? e : 1u) - e_lo;
+    unsigned long long a;
+    bool fast;
+    if (sh >= 0) {
+      fast = sh <= kFxWindow;
+      a = (unsigned long long)m << (sh & 15);
+    } else {  // below the window: exact only if the bits that would be shifted out are zero (0.0, small integers, ...)
+      const int r = min(-sh, 31);
+      fast = (m & ((1u << r) - 1u)) == 0u;
+      a = (unsigned long long)(m >> r);
+    }
+    if (e == 0xffu) {
+      if (bits & 0x7fffffu) {  // NaN: flag only
+        const unsigned bit = 1u << ((int)c & 31);
+        if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
+        return;
+      }
+      fast = false;  // +-inf
+    }
+    if (!fast) {  // outside the exact window: straight to the global f64 accumulator
+      atomicAdd(&gacc[(int)c], (double)v);
+      atomicAdd(&gcnt[(int)c], 1ull);
+      return;
+    }
+    const unsigned long long ap = (bits >> 31) ? (kFxBias - a) : (kFxBias + a);
+    const unsigned lo = (unsigned)ap, hi = (unsigned)(ap >> 32);
+    const int sl = ((int)c << RSHIFT) | copy;
+    const unsigned old = atomicAdd(&slo[sl], lo);
+    const unsigned carry = (unsigned)((old + lo) < lo);
+    const unsigned oh = atomicAdd(&shi[sl], (1u << kFxCountShift) + hi + carry);
+    if ((oh >> kFxCountShift) >= kFxDrain - 1) {
+      const unsigned h = atomicExch(&shi[sl], 0u);
+      if (h) to_level2(sl, h, atomicExch(&slo[sl], 0u));
+    }
+  };
+
+  const int sweep_tiles = max(4, min(kSweepTiles, (int)(((int64_t)S * 24) / (THREADS * 4))));
+  int since_sweep = 0;
+  walk_tiles<float, CT, THREADS>(tab, add_row, [&] {
+    if (++since_sweep == sweep_tiles) {
+      since_sweep = 0;
+      for (int sl = threadIdx.x; sl < S; sl += THREADS) {
+        const unsigned h = atomicExch(&shi[sl], 0u);
+        if (h) to_level2(sl, h, atomicExch(&slo[sl], 0u));
+      }
+    }
+  });
+  __syncthreads();
+
+  for (int g = threadIdx.x; g < G; g += THREADS) {
+    double tot = 0.0;
+    unsigned long long c = 0ull;
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const int s = (g << RSHIFT) | ((r + threadIdx.x) & (R - 1));
+      const unsigned h = shi[s];
+      const unsigned c2 = WS ? __ldcg(&stot[s]) : stot[s];
+      if (h | c2) {
+        tot += (WS ? __ldcg(&sacc[s]) : sacc[s]) + (double)fx_value(h, slo[s]) * scale;
+        c += (unsigned long long)(h >> kFxCountShift) + c2;
+      }
+    }
+    if (c) {
+      atomicAdd(&gacc[g], tot);
+      atomicAdd(&gcnt[g], c);
+    }
+    if (snanbits[g >> 5] & (1u << (g & 31))) atomicAdd(&gnan[g], 1ull);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // L2-atomic path: any A, B, G
 // ------------------------------------------------------------------------------------------
 template <typename VT, typename CT, int OP>
@@ -378,7 +522,7 @@ constexpr int kSmemThreads = 1024;
 constexpr size_t kSmemBudget = 227 * 1024;
 
 template <typename VT, int OP> size_t smem_bytes_moments(int64_t G) {
-  return (size_t)G * (sizeof(typename Slot<VT, OP>::type) + 4 + (is_float<VT>::value ? 4 : 0));
+  return (size_t)G * (sizeof(typename Acc<VT>::type) + 4 + (is_float<VT>::value ? 4 : 0));
 }
 
 template <typename VT, typename CT, int OP>
@@ -399,7 +543,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   const bool use_ws = kTwoLevel && workspace != nullptr && workspace_bytes >= (int64_t)sm_count() * (G * 12 + 8);
   const size_t smem = kTwoLevel ? (size_t)G * (use_ws ? 8 : 20) + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
   bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
-  if (force_path == 1 && !use_smem) return FLOXB_EINVAL;
+  if ((force_path == 1 || force_path == 3) && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
 
   if (use_smem) {
@@ -411,10 +555,25 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
     size_t smem_used = smem;
     if constexpr (kTwoLevel) {
       auto bytes = [&](int r) { return (size_t)G * r * 20 + (size_t)((G + 31) / 32) * 4; };
-      if (bytes(32) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 5, false>; smem_used = bytes(32); }
-      else if (bytes(8) <= kSmemBudget) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 3, false>; smem_used = bytes(8); }
-      else if (use_ws) { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, true>; }
-      else { kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, false>; }
+      // f32 sums: fixed-point level 1 (two native atomics per row); force_path 3 = the CAS-loop level 1 (sums of
+      // squares always use it: a squared f32 has a 48-bit significand)
+      constexpr bool kFx = OP == FLOXB_OP_SUM;
+      const bool fx = kFx && force_path != 3;
+      if (bytes(32) <= kSmemBudget) {
+        kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 5, false>;
+        if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 5, false>;
+        smem_used = bytes(32);
+      } else if (bytes(8) <= kSmemBudget) {
+        kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 3, false>;
+        if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 3, false>;
+        smem_used = bytes(8);
+      } else if (use_ws) {
+        kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, true>;
+        if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 0, true>;
+      } else {
+        kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 0, false>;
+        if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 0, false>;
+      }
     } else {
       kern = k_moments_smem<VT, CT, OP, kSmemThreads, 0>;
       if (smem * 32 <= kSmemBudget) { kern = k_moments_smem<VT, CT, OP, kSmemThreads, 5>; smem_used = smem * 32; }

@@ -24,7 +24,7 @@ _MINMAX = {"max": (True, False), "nanmax": (True, True), "min": (False, False), 
 _ARG = {"argmax": (True, False), "nanargmax": (True, True), "argmin": (False, False), "nanargmin": (False, True)}
 _VAR = {"var": (False, False), "nanvar": (True, False), "std": (False, True), "nanstd": (True, True)}
 
-SUPPORTED = tuple(_SUMLIKE) + tuple(_MINMAX) + tuple(_ARG) + tuple(_VAR) + ("nanlen", "mean", "nanmean", "len")
+SUPPORTED = tuple(_SUMLIKE) + tuple(_MINMAX) + tuple(_ARG) + tuple(_VAR) + ("nanlen", "mean", "nanmean")
 
 _KERNEL_OUT = (torch.float32, torch.float64, torch.int32, torch.int64)
 
@@ -67,9 +67,9 @@ def evaluate(acc: GroupedAccumulators, func: str, *, out_dtype, fill_value=None,
         op, skipna = _SUMLIKE[func]
         a, cnt, nnan = acc.moments(op, as_float)
         res = acc.finalize(L.FIN_SUM, a, None, cnt, nnan, skipna=skipna, value_dtype=fdt, **kw)
-    elif func in ("nanlen", "len"):
+    elif func == "nanlen":
         cnt, nnan = acc.counts()
-        res = acc.finalize(L.FIN_NANLEN if func == "nanlen" else L.FIN_COUNT_ALL, None, None, cnt, nnan, skipna=True, **kw)
+        res = acc.finalize(L.FIN_NANLEN, None, None, cnt, nnan, skipna=True, **kw)
     elif func in ("mean", "nanmean"):
         a, cnt, nnan = acc.moments(L.OP_SUM, as_float)
         res = acc.finalize(L.FIN_MEAN, a, None, cnt, nnan, skipna=func == "nanmean", value_dtype=fdt, **kw)

@@ -55,7 +55,6 @@ extern "C" {
 #define FLOXB_FIN_VAR 5     /* M2/(n-ddof)                     (aggregations.py:460-468)   */
 #define FLOXB_FIN_STD 6     /* sqrt of the above               (aggregations.py:471-472)   */
 #define FLOXB_FIN_ARG 7     /* index acc -> out, fill where no winner                       */
-#define FLOXB_FIN_COUNT_ALL 8 /* cnt+nnan -> out (rows with a valid label)                 */
 
 /* floxb_combine kind (flox/dask.py:131-143 with agg.simple_combine = np.sum/np.max/np.min) */
 #define FLOXB_COMB_SUM 0
@@ -92,7 +91,8 @@ int floxb_max_chunks_per_launch(void);
  *              (an exact NaN count on the L2-atomic and column paths, the number of CTAs that saw a
  *              NaN on the shared-memory f32 path)
  *   init       1 = reset the accumulators first (0 / 1 for PROD), 0 = accumulate on top
- *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics (testing / profiling)
+ *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics, 3 = shared-memory bins with the f32 CAS-loop
+ *              level 1 instead of the fixed-point one (testing / profiling)
  *   workspace  optional scratch, see floxb_moments_workspace_bytes */
 int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
                   int64_t A, int64_t B, int64_t n_groups, int op, void* acc, int64_t* cnt,

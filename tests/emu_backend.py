@@ -220,8 +220,6 @@ class EmuKernels:
                 r = np.where(rows == 0, fillv, np.where(poisoned, nan, _np(acc).astype(odt)))
             elif kind == 1:  # NANLEN
                 r = np.where(rows == 0, fillv, c.astype(odt))
-            elif kind == 8:  # COUNT_ALL
-                r = rows.astype(odt)
             elif kind == 2:  # MEAN
                 a = _np(acc)
                 s = a.astype(np.float32).astype(np.float64) if odt == np.float32 else a.astype(np.float64)

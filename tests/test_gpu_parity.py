@@ -328,6 +328,59 @@ def test_f32_two_level_accuracy_under_skew(ngroups):
         assert rel < 1e-6, (name, ngroups, rel)
 
 
+@pytest.mark.parametrize("ngroups", [7, 1000, 10_000, 25_000])
+@pytest.mark.parametrize("labels", ["random", "one_group", "sorted"])
+def test_f32_fixed_point_level1(ngroups, labels, _cuda_backend):
+    """k_moments_smem_fx (csrc/moments.cu): the integer level 1 is EXACT or not taken.  Mixed signs, zeros, exact small
+    integers far below the window, denormals, +-inf, 30 decades of magnitudes (most of those rows take the direct f64
+    path), one group receiving every row (the drain path, thousands of same-address adds in flight), sorted labels —
+    against an f64 index_add_, for both level-1 kernels (force_path 3 = the CAS-loop one)."""
+    gen = torch.Generator(device="cuda").manual_seed(2024)
+    N = 6_000_011
+    if labels == "random":
+        by = torch.randint(0, ngroups, (N,), device="cuda", generator=gen, dtype=torch.int64)
+    elif labels == "one_group":
+        by = torch.full((N,), ngroups - 1, device="cuda", dtype=torch.int64)
+    else:
+        by = torch.sort(torch.randint(0, ngroups, (N,), device="cuda", generator=gen, dtype=torch.int64)).values
+    by[::1009] = -1
+    cases = {
+        "uniform": torch.rand(N, device="cuda", generator=gen),
+        "signed": torch.randn(N, device="cuda", generator=gen) * 300.0,
+        "kelvin": 250.0 + 70.0 * torch.rand(N, device="cuda", generator=gen),
+        "wide": (torch.exp(14.0 * torch.randn(N, device="cuda", generator=gen)) *
+                 torch.sign(torch.randn(N, device="cuda", generator=gen))).to(torch.float32),
+    }
+    mixed = torch.rand(N, device="cuda", generator=gen) * 8.0 - 4.0
+    mixed[::3] = 0.0
+    mixed[1::7] = torch.randint(-5, 6, (mixed[1::7].numel(),), device="cuda", generator=gen).to(torch.float32) * 2.0 ** -20
+    mixed[2::11] = 1e-41            # denormal
+    mixed[5::13] = -3e-39           # denormal
+    mixed[4::1000] = 2.0 ** 60      # far above the window
+    cases["mixed"] = mixed
+    valid = by >= 0
+    for name, x in cases.items():
+        exact = torch.zeros(ngroups, dtype=torch.float64, device="cuda").index_add_(0, by[valid], x[valid].to(torch.float64))
+        scale = torch.zeros(ngroups, dtype=torch.float64, device="cuda").index_add_(0, by[valid], x[valid].abs().to(torch.float64))
+        cnt = torch.bincount(by[valid], minlength=ngroups)
+        for path, tol in ((0, 2e-11), (3, 5e-7)):  # 2e-11: the f64 atomics of the checker itself
+            _cuda_backend.force_path = path
+            got, _ = flox_b200.groupby_reduce(x, by, func="sum", expected_groups=np.arange(ngroups), dtype=np.float64)
+            c, _ = flox_b200.groupby_reduce(x, by, func="count", expected_groups=np.arange(ngroups))
+            torch.testing.assert_close(c, cnt, rtol=0, atol=0)
+            err = ((got - exact).abs() / scale.clamp_min(1e-300)).max().item()
+            assert err < tol, (name, labels, ngroups, path, err)
+    _cuda_backend.force_path = 0
+    # infinities and NaNs propagate like the reference's (NaN-propagating sum, nansum skips)
+    x = torch.rand(N, device="cuda", generator=gen)
+    by = torch.randint(0, ngroups, (N,), device="cuda", generator=gen, dtype=torch.int64)
+    x[10], x[11], x[12] = float("inf"), float("-inf"), float("nan")
+    by[10], by[11], by[12] = 0, 1 % ngroups, 2 % ngroups
+    got, _ = flox_b200.groupby_reduce(x, by, func="sum", expected_groups=np.arange(ngroups))
+    want = torch.zeros(ngroups, dtype=torch.float64, device="cuda").index_add_(0, by, x.to(torch.float64)).to(torch.float32)
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=0, equal_nan=True)
+
+
 # ---- size-independent properties at (near) full size -----------------------------------------------
 
 def test_full_size_properties():
