@@ -246,6 +246,46 @@ __device__ __forceinline__ void walk_flat(const VT* __restrict__ row, const CT* 
   }
 }
 
+// Walk over `values[n, B]` for a SMALL power-of-two B (2..32) so that every thread stays in ONE column and sees the rows
+// in order: lane = (row within the warp's row group) * B + column, a warp reads 32 consecutive elements (one fully
+// coalesced request) per step and owns SEG_STEPS consecutive steps (a segment of SEG_STEPS * 32/B consecutive rows), U steps
+// in flight.  `elem(v, code, row)` runs for every element in row order per thread, `segment_end()` after the last element
+// of each segment.  With sorted or blocked labels (flox's method="blockwise": rechunk.py:158-223 puts every group in one
+// block) a thread sees long runs of one code and can keep the running result in registers: one flush per RUN, not per
+// element.  Rows whose code is outside [0, G) are passed through (the caller's run logic skips them).
+template <int B, int U, int SEG_STEPS, typename VT, typename CT, typename Elem, typename SegEnd>
+__device__ __forceinline__ void walk_rows_small_b(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t n,
+                                                  Elem elem, SegEnd segment_end) {
+  static_assert(B >= 1 && B <= 32 && (B & (B - 1)) == 0, "B must be a power of two <= 32");
+  static_assert(SEG_STEPS % U == 0, "segment steps must be a multiple of the unroll");
+  constexpr int RW = 32 / B;  // rows per warp step
+  const int lane = threadIdx.x & 31;
+  const int rw = lane / B;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr int64_t SEG_ROWS = (int64_t)SEG_STEPS * RW;
+  for (int64_t seg0 = warp * SEG_ROWS; seg0 < n; seg0 += warps * SEG_ROWS) {
+    const int64_t seg1 = seg0 + SEG_ROWS < n ? seg0 + SEG_ROWS : n;
+    for (int64_t r0 = seg0 + rw; r0 < seg1; r0 += (int64_t)U * RW) {
+      VT v[U];
+      CT c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * RW;
+        const bool ok = r < seg1;
+        c[u] = ok ? codes[r] : (CT)-1;
+        v[u] = ok ? vals[r * B + (lane & (B - 1))] : VT(0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t r = r0 + (int64_t)u * RW;
+        if (r < seg1) elem(v[u], c[u], r);
+      }
+    }
+    segment_end();
+  }
+}
+
 // Host side: fill `tab` with chunks [c0, c0 + m) and return the number of tiles (of `tile` rows) they hold, or a
 // negative FLOXB_E* code.
 inline int64_t fill_chunk_table(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t c0, int64_t tile, ChunkTable* tab) {

@@ -278,7 +278,7 @@ k_moments_smem_fx(const __grid_constant__ ChunkTable tab, int G, double* __restr
   unsigned* slo = reinterpret_cast<unsigned*>(smem_raw + (WS ? 0 : (size_t)S * 12));  // [S]
   unsigned* shi = slo + S;                                                             // [S]
   unsigned* snanbits = shi + S;                                                        // [NW]
-  __shared__ int s_emax;
+  int& s_emax = *reinterpret_cast<int*>(snanbits + NW);  // dynamic too: static + dynamic must fit the 227 KB opt-in
   const int copy = threadIdx.x & (R - 1);
   if (threadIdx.x == 0) s_emax = 0;
   for (int s = threadIdx.x; s < S; s += THREADS) {
@@ -506,6 +506,48 @@ k_moments_global_runs(const VT* __restrict__ vals, const CT* __restrict__ codes,
   }
 }
 
+// L2-atomic path for a SMALL power-of-two number of kept trailing columns (BASELINE config 4: f64 (1e8, 8), G = 1e5,
+// method="blockwise"): every thread keeps one column's running (sum, count, NaN count) in registers while the code does
+// not change (walk_rows_small_b) and issues one RED set per RUN.  Blockwise / sorted labels: ~1 RED set per
+// thread per 64-step segment instead of one per element, the kernel becomes an HBM stream; random labels: one set per
+// element, like k_moments_global.  Accumulators are group-major [G][A*B] like every B > 1 kernel.
+template <typename VT, typename CT, int OP, int B>
+__global__ void __launch_bounds__(256)
+k_moments_global_bruns(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t G,
+                       typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
+                       unsigned long long* __restrict__ gnan) {
+  using AccT = typename Acc<VT>::type;
+  const AccT ident = (OP == FLOXB_OP_PROD) ? (AccT)1 : (AccT)0;
+  const int col = threadIdx.x & (B - 1);
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    const int64_t ab = a * B + col, AB = A * B;
+    long long cur = -1;
+    AccT s = ident;
+    unsigned cn = 0, mn = 0;
+    auto flush = [&] {
+      if ((unsigned long long)cur < (unsigned long long)G) {
+        const int64_t bin = (int64_t)cur * AB + ab;
+        if (cn) {
+          if constexpr (OP == FLOXB_OP_PROD) atomic_mul(&gacc[bin], s); else atomic_add(&gacc[bin], s);
+          atomicAdd(&gcnt[bin], (unsigned long long)cn);
+        }
+        if (mn) atomicAdd(&gnan[bin], (unsigned long long)mn);
+      }
+      s = ident; cn = 0; mn = 0;
+    };
+    walk_rows_small_b<B, 8, 64>(vals + a * n * B, codes, n,
+      [&](VT v, CT c, int64_t) {
+        if ((long long)c != cur) { flush(); cur = (long long)c; }
+        if (is_nan(v)) ++mn;
+        else {
+          if constexpr (OP == FLOXB_OP_PROD) s *= lift<VT, OP>(v); else s += lift<VT, OP>(v);
+          ++cn;
+        }
+      },
+      [&] { flush(); cur = -1; });
+  }
+}
+
 template <typename AccT>
 __global__ void k_fill_acc(AccT* acc, unsigned long long* cnt, unsigned long long* nnan, int64_t nbins, AccT ident) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (int64_t)gridDim.x * blockDim.x) {
@@ -542,7 +584,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
   constexpr bool kTwoLevel = std::is_same<VT, float>::value && OP != FLOXB_OP_PROD;
   const bool use_ws = kTwoLevel && workspace != nullptr && workspace_bytes >= (int64_t)sm_count() * (G * 12 + 8);
   const size_t smem = kTwoLevel ? (size_t)G * (use_ws ? 8 : 20) + (size_t)((G + 31) / 32) * 4 : smem_bytes_moments<VT, OP>(G);
-  bool use_smem = (A == 1 && B == 1 && smem <= kSmemBudget);
+  bool use_smem = (A == 1 && B == 1 && smem + (kTwoLevel ? 16 : 0) <= kSmemBudget);
   if ((force_path == 1 || force_path == 3) && !use_smem) return FLOXB_EINVAL;
   if (force_path == 2) use_smem = false;
 
@@ -559,11 +601,11 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
       // squares always use it: a squared f32 has a 48-bit significand)
       constexpr bool kFx = OP == FLOXB_OP_SUM;
       const bool fx = kFx && force_path != 3;
-      if (bytes(32) <= kSmemBudget) {
+      if (bytes(32) + 16 <= kSmemBudget) {
         kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 5, false>;
         if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 5, false>;
         smem_used = bytes(32);
-      } else if (bytes(8) <= kSmemBudget) {
+      } else if (bytes(8) + 16 <= kSmemBudget) {
         kern_ws = k_moments_smem_f32<CT, OP, kSmemThreads, 3, false>;
         if constexpr (kFx) if (fx) kern_ws = k_moments_smem_fx<CT, kSmemThreads, 3, false>;
         smem_used = bytes(8);
@@ -592,7 +634,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
       const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
       if (kern_ws) {
         if constexpr (kTwoLevel)
-          kern_ws<<<grid, kSmemThreads, smem_used, st>>>(tab, (int)G, gacc, gcnt, gnan, reinterpret_cast<double*>(workspace));
+          kern_ws<<<grid, kSmemThreads, smem_used + 16, st>>>(tab, (int)G, gacc, gcnt, gnan, reinterpret_cast<double*>(workspace));
       } else {
         kern<<<grid, kSmemThreads, smem_used, st>>>(tab, (int)G, gacc, gcnt, gnan);
       }
@@ -614,6 +656,23 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
         k_moments_global_runs<VT, CT, OP><<<grid, 256, 0, st>>>(reinterpret_cast<const VT*>(ch.values),
                                                               reinterpret_cast<const CT*>(ch.codes), A, ch.n, G, gacc,
                                                               gcnt, gnan);
+      } else if (B <= 32 && (B & (B - 1)) == 0 && force_path != 4) {
+        // small power-of-two B: run-merging kernel, one warp per segment of 64 steps
+        const int64_t segs = (ch.n * B + 64 * 32 - 1) / (64 * 32);
+        int64_t gx = (segs + 7) / 8;  // 8 warps per block
+        if (gx > cap) gx = cap;
+        if (gx * by > cap * 4) gx = (cap * 4 + by - 1) / by;
+        if (gx < 1) gx = 1;
+        dim3 g2((unsigned)gx, (unsigned)by);
+        const VT* v = reinterpret_cast<const VT*>(ch.values);
+        const CT* c = reinterpret_cast<const CT*>(ch.codes);
+        switch (B) {
+          case 2: k_moments_global_bruns<VT, CT, OP, 2><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+          case 4: k_moments_global_bruns<VT, CT, OP, 4><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+          case 8: k_moments_global_bruns<VT, CT, OP, 8><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+          case 16: k_moments_global_bruns<VT, CT, OP, 16><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+          default: k_moments_global_bruns<VT, CT, OP, 32><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+        }
       } else {
         k_moments_global<VT, CT, OP><<<grid, 256, 0, st>>>(reinterpret_cast<const VT*>(ch.values),
                                                          reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, gacc,

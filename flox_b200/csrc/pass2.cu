@@ -113,6 +113,39 @@ k_sqdev_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_
   }
 }
 
+// Small power-of-two B (config 4): the thread keeps its column's running sum of squared deviations in a register
+// while the code does not change and issues ONE RED per run (walk_rows_small_b; see k_moments_global_bruns).
+template <typename VT, typename CT, int B>
+__global__ void __launch_bounds__(256)
+k_sqdev_global_bruns(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t G,
+                     const double* __restrict__ means, int skipna, double* __restrict__ gm2) {
+  const int col = threadIdx.x & (B - 1);
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    const int64_t ab = a * B + col, AB = A * B;
+    long long cur = -1;
+    double s = 0.0, mean = 0.0;
+    bool any = false;
+    auto flush = [&] {
+      if (any) atomicAdd(&gm2[(int64_t)cur * AB + ab], s);
+      s = 0.0;
+      any = false;
+    };
+    walk_rows_small_b<B, 8, 64>(vals + a * n * B, codes, n,
+      [&](VT v, CT c, int64_t) {
+        if ((long long)c != cur) {
+          flush();
+          cur = (long long)c;
+          if ((unsigned long long)cur < (unsigned long long)G) mean = means[(int64_t)cur * AB + ab];
+        }
+        if ((unsigned long long)cur >= (unsigned long long)G || (is_nan(v) && skipna)) return;
+        const double d = (double)v - mean;
+        s += d * d;
+        any = true;
+      },
+      [&] { flush(); cur = -1; });
+  }
+}
+
 // ---- arg-extremum ------------------------------------------------------------------------
 template <typename VT, typename CT>
 __global__ void __launch_bounds__(256)
@@ -175,8 +208,20 @@ int launch_sqdev(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64
       const floxb_chunk_t& ch = chunks[k];
       if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
       if (ch.n == 0) continue;
-      k_sqdev_global<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(
-          reinterpret_cast<const VT*>(ch.values), reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, means, skipna, m2);
+      const VT* v = reinterpret_cast<const VT*>(ch.values);
+      const CT* c = reinterpret_cast<const CT*>(ch.codes);
+      if (B > 1 && B <= 32 && (B & (B - 1)) == 0) {
+        const dim3 g2 = generic_grid((ch.n * B + 7) / 8, A);  // one warp per 64-step segment, 8 warps per block
+        switch (B) {
+          case 2: k_sqdev_global_bruns<VT, CT, 2><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, means, skipna, m2); break;
+          case 4: k_sqdev_global_bruns<VT, CT, 4><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, means, skipna, m2); break;
+          case 8: k_sqdev_global_bruns<VT, CT, 8><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, means, skipna, m2); break;
+          case 16: k_sqdev_global_bruns<VT, CT, 16><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, means, skipna, m2); break;
+          default: k_sqdev_global_bruns<VT, CT, 32><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, means, skipna, m2); break;
+        }
+        continue;
+      }
+      k_sqdev_global<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(v, c, A, ch.n, B, G, means, skipna, m2);
     }
   }
   return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;

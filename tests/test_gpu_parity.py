@@ -292,6 +292,35 @@ def test_row_batched_layout_warp_per_row_kernels(dtype, ngroups, T):
         assert_same(got, want, what=f"rows/{func}/{np.dtype(dtype)}/{ngroups}", **_tols(func, arr))
 
 
+@pytest.mark.parametrize("labels", ["random", "sorted", "blocked"])
+@pytest.mark.parametrize("B", [2, 8, 32, 3])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_small_trailing_dims_huge_G(dtype, B, labels):
+    """BASELINE config 4's layout at oracle-sized n: (n, B) values with NaNs handed over as the (B, n) view, G = 1e5,
+    labels random / sorted / blocked (method="blockwise": every group in one contiguous block, blocks in random order).
+    Power-of-two B <= 32 takes the run-merging kernels (k_moments_global_bruns, k_sqdev_global_bruns), B = 3 the
+    per-element L2-atomic ones; both must agree with the oracle."""
+    rng = np.random.default_rng(404)
+    n, G = 300_007, 100_000
+    base = rng.standard_normal((n, B)).astype(dtype) * 3 + 1
+    base.reshape(-1)[::7] = np.nan
+    by = rng.integers(0, G, n)
+    if labels == "sorted":
+        by = np.sort(by)
+    elif labels == "blocked":
+        order = rng.permutation(G)
+        by = order[np.sort(by)]
+    by[::501] = -1
+    view = base.T
+    xt = torch.as_tensor(base, device="cuda").t()
+    bt = torch.as_tensor(by, device="cuda")
+    for func in ("nansum", "sum", "count", "nanvar", "var", "nanmax", "nanmean"):
+        fk = {"ddof": 1} if "var" in func else None
+        want, _ = O.groupby_reduce(np.ascontiguousarray(view), by, func=func, ddof=1 if fk else 0, expected_groups=np.arange(G))
+        got, _ = flox_b200.groupby_reduce(xt, bt, func=func, finalize_kwargs=fk, expected_groups=np.arange(G))
+        assert_same(got.cpu().numpy(), want, what=f"c4/{func}/{np.dtype(dtype)}/B{B}/{labels}", **_tols(func, base))
+
+
 def test_torch_cuda_inputs_stay_on_device():
     rng = np.random.default_rng(5)
     x = rng.random(300_000).astype(np.float32)
@@ -368,7 +397,9 @@ def test_f32_fixed_point_level1(ngroups, labels, _cuda_backend):
             got, _ = flox_b200.groupby_reduce(x, by, func="sum", expected_groups=np.arange(ngroups), dtype=np.float64)
             c, _ = flox_b200.groupby_reduce(x, by, func="count", expected_groups=np.arange(ngroups))
             torch.testing.assert_close(c, cnt, rtol=0, atol=0)
-            err = ((got - exact).abs() / scale.clamp_min(1e-300)).max().item()
+            present = cnt > 0  # absent groups hold the NaN fill
+            assert bool(torch.isnan(got[~present]).all())
+            err = ((got - exact).abs() / scale.clamp_min(1e-300))[present].max().item()
             assert err < tol, (name, labels, ngroups, path, err)
     _cuda_backend.force_path = 0
     # infinities and NaNs propagate like the reference's (NaN-propagating sum, nansum skips)

@@ -98,10 +98,14 @@ def main():
         x.view(-1)[::7] = float("nan")
         by = torch.randint(0, G, (n,), device=dev, generator=gen)
         view = x.t()  # (8, n): reduced axis last, memory is (n, 8)
-        for func in ("nansum", "nanvar"):
-            best, mean = timeit(lambda: flox_b200.groupby_reduce(view, by, func=func, expected_groups=np.arange(G)), reps=3, warm=1)
-            passes = 2 if "var" in func else 1
-            report(f"C4 f64 (1e8,8) NaNs G=1e5 {func}", n * B * passes, 9, best, mean, f"{passes} pass(es) over the data, L2-atomic path")
+        # method="blockwise" means every group lives in ONE block (rechunk.py:158-223): sorted labels are that layout;
+        # random labels are the worst case for the same call
+        for lname, lab in (("sorted (blockwise layout)", torch.sort(by).values), ("random", by)):
+            for func in ("nansum", "nanvar"):
+                best, mean = timeit(lambda: flox_b200.groupby_reduce(view, lab, func=func, expected_groups=np.arange(G)), reps=3, warm=1)
+                passes = 2 if "var" in func else 1
+                report(f"C4 f64 (1e8,8) NaNs G=1e5 {func}, labels {lname}", n * B * passes, 9, best, mean,
+                       f"{passes} pass(es) over the data, L2-atomic path, run-merging kernels (force_path={os.environ.get('FLOXB_FORCE_PATH', '0')})")
         del x, view
         torch.cuda.empty_cache()
 
