@@ -54,7 +54,17 @@ SIGNATURES = {
     "floxb_lut_codes": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "floxb_host_pack_codes": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32]),
     "floxb_widen_codes": (_i32, [_vp, _i64, _vp, _vp]),
+    "floxb_ipc_alloc": (_i32, [_i64, C.POINTER(_vp), _vp]),
+    "floxb_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
+    "floxb_ipc_close": (_i32, [_vp]),
+    "floxb_ipc_free": (_i32, [_vp]),
+    "floxb_xchg_allreduce": (_i32, [C.POINTER(_vp), _i32, _i32, C.c_uint64, _i64, _i32, C.POINTER(_i64), C.POINTER(_i32),
+                                    C.POINTER(_vp), _vp]),
+    "floxb_xchg_status": (_i32, [_vp, C.POINTER(C.c_uint64)]),
 }
+
+XCHG_MAX_RANKS, XCHG_MAX_SEGMENTS, XCHG_HEADER_BYTES = 8, 4, 128
+XCHG_SUM_F64, XCHG_SUM_I64, XCHG_MAX_I64, XCHG_MIN_I64, XCHG_PROD_F64, XCHG_PROD_I64 = range(6)
 
 _lock = threading.Lock()
 _lib = None

@@ -15,13 +15,13 @@ from typing import Sequence
 import torch
 
 from . import _lib as L
-from .kernels import acc_dtype, get_kernels
+from .kernels import PreparedChunks, acc_dtype, get_kernels
 
 
 class GroupedAccumulators:
     def __init__(self, chunks: Sequence[tuple[torch.Tensor, torch.Tensor]], A: int, B: int, G: int,
                  value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None, comm=None):
-        self.chunks = list(chunks)
+        self.chunks = chunks if isinstance(chunks, PreparedChunks) else list(chunks)
         self.A, self.B, self.G = int(A), int(B), int(G)
         self.nbins = self.A * self.B * self.G
         self.value_dtype = value_dtype
@@ -56,6 +56,45 @@ class GroupedAccumulators:
         """(both, cnt, nnan): the two i64 counters share one buffer so that ranks merge them with ONE collective."""
         both = torch.empty(2 * self.nbins, dtype=torch.int64, device=self.device)
         return both, both[: self.nbins], both[self.nbins:]
+
+    def _acc_and_counts(self, dtype: torch.dtype):
+        """(px, acc, both, cnt, nnan).  With several ranks and a small bin count the accumulators live in the NVLink
+        peer-exchange buffer (px is the PeerExchange): the kernels accumulate straight into it and ONE launch merges
+        value accumulator and counters across ranks (flox_b200/exchange.py)."""
+        px = self.comm.peer(24 * self.nbins, self.device) if (self.comm and self.nbins) else None
+        if px is not None:
+            acc, both = px.views([(dtype, self.nbins), (torch.int64, 2 * self.nbins)])
+        else:
+            acc = torch.empty(self.nbins, dtype=dtype, device=self.device)
+            both = torch.empty(2 * self.nbins, dtype=torch.int64, device=self.device)
+        return px, acc, both, both[: self.nbins], both[self.nbins:]
+
+    def _merge(self, px, acc, both, how: str):
+        """Cross-rank merge of one pass (flox's combine stage, flox/dask.py:90-144): `how` for the value accumulator,
+        sum for the counters.  Returns (acc, cnt, nnan)."""
+        if self.comm:
+            if px is not None:
+                acc, both = px.merge([acc, both], [how, "sum"])
+            else:
+                {"sum": self.comm.sum_, "prod": self.comm.prod_, "max": self.comm.max_, "min": self.comm.min_}[how](acc)
+                self.comm.sum_(both)
+        return acc, both[: self.nbins], both[self.nbins:]
+
+    def _single(self, dtype: torch.dtype):
+        px = self.comm.peer(8 * self.nbins, self.device) if (self.comm and self.nbins) else None
+        if px is not None:
+            (t,) = px.views([(dtype, self.nbins)])
+        else:
+            t = torch.empty(self.nbins, dtype=dtype, device=self.device)
+        return px, t
+
+    def _merge_single(self, px, t, how: str):
+        if self.comm:
+            if px is not None:
+                (t,) = px.merge([t], [how])
+            else:
+                {"sum": self.comm.sum_, "min": self.comm.min_}[how](t)
+        return t
 
     # ---- kernel families -----------------------------------------------------------------
     def _chunks_as(self, as_float: bool):
@@ -109,31 +148,23 @@ class GroupedAccumulators:
         as_float = bool(as_float) and not self.value_dtype.is_floating_point
         if (op, as_float) not in self._moments:
             chunks, vdt = self._chunks_as(as_float)
-            acc = torch.empty(self.nbins, dtype=acc_dtype(vdt), device=self.device)
-            both, cnt, nnan = self._count_pair()
+            px, acc, both, cnt, nnan = self._acc_and_counts(acc_dtype(vdt))
             if self._use_cols():
                 self._reduce_cols(chunks, op, acc, cnt, nnan, self.B > 1)
             else:
                 self.k.moments(chunks, self.A, self.B, self.G, op, acc, cnt, nnan, init=True)
-            if self.comm:
-                (self.comm.prod_ if op == L.OP_PROD else self.comm.sum_)(acc)
-                self.comm.sum_(both)
-            self._moments[(op, as_float)] = (acc, cnt, nnan)
+            self._moments[(op, as_float)] = self._merge(px, acc, both, "prod" if op == L.OP_PROD else "sum")
         return self._moments[(op, as_float)]
 
     def minmax(self, is_max: bool):
         if is_max not in self._minmax:
-            key = self._i64()
-            both, cnt, nnan = self._count_pair()
+            px, key, both, cnt, nnan = self._acc_and_counts(torch.int64)
             if self._use_cols():
                 self._reduce_cols(self.chunks, 3 if is_max else 4, key, cnt, nnan, self.B > 1)
             else:
                 self.k.minmax(self.chunks, self.A, self.B, self.G, is_max, key, cnt, nnan, init=True,
                               value_dtype=self.value_dtype)
-            if self.comm:
-                (self.comm.max_ if is_max else self.comm.min_)(key)
-                self.comm.sum_(both)
-            self._minmax[is_max] = (key, cnt, nnan)
+            self._minmax[is_max] = self._merge(px, key, both, "max" if is_max else "min")
         return self._minmax[is_max]
 
     def counts(self):
@@ -150,13 +181,13 @@ class GroupedAccumulators:
         if skipna not in self._var:
             chunks, vdt = self._chunks_as(True)
             acc, cnt, nnan = self.moments(L.OP_SUM, as_float=True)
-            means, m2 = self._f64(), self._f64()
+            means = self._f64()
+            px, m2 = self._single(torch.float64)
             self.k.group_means(vdt, acc, cnt, nnan, skipna, means)
             # means come from the ALREADY MERGED sums, so M2 is about the global group mean and the
             # cross-rank merge is a plain sum (no Chan adjustment terms needed, cf. aggregations.py:392-451)
             self.k.sqdev(chunks, self.A, self.B, self.G, means, skipna, m2, init=True, value_dtype=vdt)
-            if self.comm:
-                self.comm.sum_(m2)
+            m2 = self._merge_single(px, m2, "sum")
             self._var[skipna] = (m2, acc, cnt, nnan)
         return self._var[skipna]
 
@@ -164,12 +195,11 @@ class GroupedAccumulators:
         key_ = (is_max, skipna)
         if key_ not in self._arg:
             key, cnt, nnan = self.minmax(is_max)
-            idx = self._i64()
+            px, idx = self._single(torch.int64)
             self.k.argext(self.chunks, self.A, self.B, self.G, key, nnan, skipna, self.index_base, idx, init=True,
                           value_dtype=self.value_dtype)
-            if self.comm:  # key / nnan are already global, so local candidates are comparable
-                self.comm.min_(idx)
-            self._arg[key_] = idx
+            # key / nnan are already global, so local candidates are comparable
+            self._arg[key_] = self._merge_single(px, idx, "min")
         return self._arg[key_]
 
     # ---- typed results -------------------------------------------------------------------

@@ -92,4 +92,10 @@ def var_combine_stacked(m2, s, n, axis: int, keepdims: bool = True):
         parts.append(st)
     outs = [torch.empty(parts[0].shape[1], dtype=torch.float64, device=tm2.device) for _ in range(3)]
     get_kernels().var_combine(parts[0], parts[1], parts[2], *outs)
-    return tuple(from_device(_restore(o, tm2.shape, axes, kept_shape, keepdims).to(tm2.dtype), like, np_dt) for o in outs)
+    # dtypes as the reference produces them: S and n keep the intermediate dtype, the merged M2 is float64 as soon as
+    # more than one block is merged (the adjustment terms divide by an integer-augmented denominator,
+    # aggregations.py:427-436: float32 / (float32 + int64) -> float64)
+    nblk = parts[0].shape[0]
+    dts = [(torch.float64, np.dtype("float64")) if (k == 0 and nblk > 1) else (tm2.dtype, np_dt) for k in range(3)]
+    return tuple(from_device(_restore(o, tm2.shape, axes, kept_shape, keepdims).to(tdt), like, ndt)
+                 for o, (tdt, ndt) in zip(outs, dts))

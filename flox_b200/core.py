@@ -374,9 +374,20 @@ def _validate_expected_groups(nby: int, expected_groups):
     return expected_groups
 
 
+_arange_seen: tuple = (None, False)
+
+
 def _is_arange(ex: np.ndarray) -> bool:
+    """0..n-1?  The O(n) check is remembered for the last array OBJECT seen (a map-reduce loop passes the same
+    expected_groups every call; at 1e6 groups the check costs more than the kernels)."""
+    global _arange_seen
+    seen = _arange_seen  # one read: other threads replace the tuple as a whole
+    if seen[0] is ex and not ex.flags.writeable:
+        return seen[1]
     n = ex.size
-    return bool(ex[0] == 0 and ex[-1] == n - 1 and (n < 3 or np.all(ex[1:] - ex[:-1] == 1)))
+    ok = bool(ex[0] == 0 and ex[-1] == n - 1 and (n < 3 or np.all(ex[1:] - ex[:-1] == 1)))
+    _arange_seen = (ex, ok)
+    return ok
 
 
 def _choose_engine(by, agg: Aggregation) -> str:

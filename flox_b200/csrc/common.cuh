@@ -160,8 +160,10 @@ __device__ __forceinline__ void atomic_add(long long* a, long long v) {
 // chunk boundaries, so the load stays balanced), with the 128-bit loads of its next tile in flight while
 // `add_row(value, code)` runs on the current one.  Chunk tails (n % TILE rows) and unaligned chunks are
 // handled afterwards by a scalar loop, spread over the CTAs.  `after_tile()` runs once per full tile.
-template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
-__device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row, AfterTile after_tile) {
+// `add_tile(Vec4 values, Vec4 codes)` handles the 4 rows a thread owns in a full tile (so that a kernel can overlap the
+// latencies of the four rows' atomics), `add_row(value, code)` the scalar leftovers.
+template <typename VT, typename CT, int THREADS, typename AddTile, typename AddRow, typename AfterTile>
+__device__ __forceinline__ void walk_tiles4(const ChunkTable& tab, AddTile add_tile, AddRow add_row, AfterTile after_tile) {
   constexpr int TILE = THREADS * 4;
   const int nch = tab.nchunks;
   auto full_tiles = [&](int k) -> int64_t {
@@ -192,8 +194,7 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row
       v1 = load4<VT>(reinterpret_cast<const VT*>(tab.values[ch]) + local * TILE + threadIdx.x * 4);
       c1 = load4<CT>(reinterpret_cast<const CT*>(tab.codes[ch]) + local * TILE + threadIdx.x * 4);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) add_row(v0.v[k], c0.v[k]);
+    add_tile(v0, c0);
     after_tile();
     v0 = v1;
     c0 = c1;
@@ -210,6 +211,14 @@ __device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row
       for (int64_t i = base + threadIdx.x; i < end; i += THREADS) add_row(vals[i], codes[i]);
     }
   }
+}
+
+template <typename VT, typename CT, int THREADS, typename AddRow, typename AfterTile>
+__device__ __forceinline__ void walk_tiles(const ChunkTable& tab, AddRow add_row, AfterTile after_tile) {
+  walk_tiles4<VT, CT, THREADS>(tab, [&](const Vec4<VT>& v, const Vec4<CT>& c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) add_row(v.v[k], c.v[k]);
+  }, add_row, after_tile);
 }
 
 // Grid-stride walk over the flat elements j = i*B + b of one `values[n, B]` slab for the L2-atomic kernels, U

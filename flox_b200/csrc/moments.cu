@@ -305,56 +305,82 @@ k_moments_smem_fx(const __grid_constant__ ChunkTable tab, int G, double* __restr
   }
   __syncthreads();
   const int e_lo = max(1, min(s_emax + 1, 254) - kFxWindow);
-  const double scale = __longlong_as_double((long long)(e_lo - 150 + 1023) << 52);  // 2^(e_lo - 150)
+  const double scale = __longlong_as_double((long long)(e_lo - 150 + 1023) << 52);  // 2^(e_lo - 150): one fixed-point unit
+  // float -> fixed point through the f64 "magic constant": C = 1.5 * 2^52 units.  d = v + C rounds v to a whole number of
+  // units and leaves that integer in d's low significand bits; (d - C) == v says that nothing was rounded away (v is an
+  // exact multiple of the unit), and the biased integer a' = bits(d) - bits(C) + 2^37 must fall in [0, 2^38) (|v| inside
+  // the window).  NaN fails the comparison, infinities and huge values the range test: they take the slow path.
+  const unsigned long long cbits = ((unsigned long long)(e_lo + 925) << 52) | (1ull << 51);
+  const double C = __longlong_as_double((long long)cbits);
+  const unsigned long long kc = cbits - kFxBias;
 
   auto to_level2 = [&](int sl, unsigned h, unsigned l) {
     atomicAdd(&sacc[sl], (double)fx_value(h, l) * scale);
     atomicAdd(&stot[sl], h >> kFxCountShift);
   };
+  auto drain = [&](int sl) {
+    const unsigned h = atomicExch(&shi[sl], 0u);
+    if (h) to_level2(sl, h, atomicExch(&slo[sl], 0u));
+  };
+  auto slow_row = [&](float v, int c) {  // outside the exact window (rare): NaN -> flag, else straight to the global f64 bins
+    if (v != v) {
+      const unsigned bit = 1u << (c & 31);
+      if (!(snanbits[c >> 5] & bit)) atomicOr(&snanbits[c >> 5], bit);
+    } else {
+      atomicAdd(&gacc[c], (double)v);
+      atomicAdd(&gcnt[c], 1ull);
+    }
+  };
+  // state: 0 = no group, 1 = two native atomics, 2 = slow path
+  auto convert = [&](float v, CT c, unsigned& lo, unsigned& hi) -> int {
+    const double vd = (double)v;
+    const double d = vd + C;
+    const unsigned long long ap = (unsigned long long)__double_as_longlong(d) - kc;
+    lo = (unsigned)ap;
+    hi = (unsigned)(ap >> 32);
+    const bool fast = ((d - C) == vd) && hi < (1u << (24 + kFxWindow + 1 - 32));
+    return ((unsigned long long)c < (unsigned long long)G) ? (fast ? 1 : 2) : 0;
+  };
   auto add_row = [&](float v, CT c) {
-    if ((unsigned long long)c >= (unsigned long long)G) return;
-    const unsigned bits = __float_as_uint(v);
-    const unsigned e = (bits >> 23) & 0xffu;
-    const unsigned m = (bits & 0x7fffffu) | (e ? 0x800000u : 0u);
-    const int sh = (int)(e ? e : 1u) - e_lo;
-    unsigned long long a;
-    bool fast;
-    if (sh >= 0) {
-      fast = sh <= kFxWindow;
-      a = (unsigned long long)m << (sh & 15);
-    } else {  // below the window: exact only if the bits that would be shifted out are zero (0.0, small integers, ...)
-      const int r = min(-sh, 31);
-      fast = (m & ((1u << r) - 1u)) == 0u;
-      a = (unsigned long long)(m >> r);
+    unsigned lo, hi;
+    const int st = convert(v, c, lo, hi);
+    if (st == 1) {
+      const int sl = ((int)c << RSHIFT) | copy;
+      const unsigned old = atomicAdd(&slo[sl], lo);
+      const unsigned oh = atomicAdd(&shi[sl], (1u << kFxCountShift) + hi + (unsigned)((old + lo) < lo));
+      if ((oh >> kFxCountShift) >= kFxDrain - 1) drain(sl);
+    } else if (st == 2) {
+      slow_row(v, (int)c);
     }
-    if (e == 0xffu) {
-      if (bits & 0x7fffffu) {  // NaN: flag only
-        const unsigned bit = 1u << ((int)c & 31);
-        if (!(snanbits[(int)c >> 5] & bit)) atomicOr(&snanbits[(int)c >> 5], bit);
-        return;
+  };
+  // the four rows of a tile in phases, so that four returning atomics are in flight per thread instead of one
+  auto add_tile = [&](const Vec4<float>& v, const Vec4<CT>& c) {
+    unsigned lo[4], hi[4], old[4], oh[4];
+    int st[4], sl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st[k] = convert(v.v[k], c.v[k], lo[k], hi[k]);
+      sl[k] = ((int)c.v[k] << RSHIFT) | copy;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (st[k] == 1) old[k] = atomicAdd(&slo[sl[k]], lo[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (st[k] == 1) oh[k] = atomicAdd(&shi[sl[k]], (1u << kFxCountShift) + hi[k] + (unsigned)((old[k] + lo[k]) < lo[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (st[k] == 1) {
+        if ((oh[k] >> kFxCountShift) >= kFxDrain - 1) drain(sl[k]);
+      } else if (st[k] == 2) {
+        slow_row(v.v[k], (int)c.v[k]);
       }
-      fast = false;  // +-inf
-    }
-    if (!fast) {  // outside the exact window: straight to the global f64 accumulator
-      atomicAdd(&gacc[(int)c], (double)v);
-      atomicAdd(&gcnt[(int)c], 1ull);
-      return;
-    }
-    const unsigned long long ap = (bits >> 31) ? (kFxBias - a) : (kFxBias + a);
-    const unsigned lo = (unsigned)ap, hi = (unsigned)(ap >> 32);
-    const int sl = ((int)c << RSHIFT) | copy;
-    const unsigned old = atomicAdd(&slo[sl], lo);
-    const unsigned carry = (unsigned)((old + lo) < lo);
-    const unsigned oh = atomicAdd(&shi[sl], (1u << kFxCountShift) + hi + carry);
-    if ((oh >> kFxCountShift) >= kFxDrain - 1) {
-      const unsigned h = atomicExch(&shi[sl], 0u);
-      if (h) to_level2(sl, h, atomicExch(&slo[sl], 0u));
     }
   };
 
   const int sweep_tiles = max(4, min(kSweepTiles, (int)(((int64_t)S * 24) / (THREADS * 4))));
   int since_sweep = 0;
-  walk_tiles<float, CT, THREADS>(tab, add_row, [&] {
+  walk_tiles4<float, CT, THREADS>(tab, add_tile, add_row, [&] {
     if (++since_sweep == sweep_tiles) {
       since_sweep = 0;
       for (int sl = threadIdx.x; sl < S; sl += THREADS) {

@@ -35,6 +35,16 @@ def acc_dtype(value_dtype: torch.dtype) -> torch.dtype:
 Chunks = Sequence[tuple[torch.Tensor, torch.Tensor]]  # (values[A, n, B], codes[n])
 
 
+class PreparedChunks(list):
+    """A chunk list whose C-ABI descriptor table (`floxb_chunk_t[]`) is built once and reused: a map-reduce loop hands the
+    same device-resident chunks to the kernels every step, and filling 100 ctypes structs per call costs more host time
+    than an 8-GPU share of the kernel runs (bench.py: host_enqueue_ms_per_step)."""
+
+    def __init__(self, chunks):
+        super().__init__(chunks)
+        self.table = None  # (ctypes array, value dtype, code dtype, A, B), filled by CudaKernels._chunk_array
+
+
 class CudaKernels:
     name = "cuda"
 
@@ -84,6 +94,15 @@ class CudaKernels:
                 raise L.FloxB200Error("flox_b200 kernels need CUDA tensors (no CPU fallback)")
 
     def _chunk_array(self, chunks: Chunks, A: int, B: int):
+        cached = getattr(chunks, "table", None)
+        if cached is not None and cached[3] == A and cached[4] == B:
+            return cached[0], cached[1], cached[2]
+        arr, vdt, cdt = self._build_chunk_array(chunks, A, B)
+        if isinstance(chunks, PreparedChunks):
+            chunks.table = (arr, vdt, cdt, A, B)
+        return arr, vdt, cdt
+
+    def _build_chunk_array(self, chunks: Chunks, A: int, B: int):
         arr = (L.Chunk * len(chunks))()
         vdt = cdt = None
         for k, (v, c) in enumerate(chunks):

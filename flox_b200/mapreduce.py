@@ -33,7 +33,7 @@ from .aggregations import Aggregation, _is_arg_reduction, is_var_chunk_reduction
 from .arrays import count_h2d, from_device, is_torch, kernel_dtype, to_device
 from .chunked import ChunkedArray, is_chunked
 from .core import DUMMY_AXIS, _finalize_results
-from .kernels import default_device, get_kernels
+from .kernels import PreparedChunks, default_device, get_kernels
 from .multiarray import MultiArray
 from .reductions import evaluate, var_triple
 from .reindex import ReindexStrategy
@@ -154,6 +154,15 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     global position of each chunk's first element along the reduced axis (only arg-reductions need
     positions that are global across ranks: that costs one small all-gather of shard lengths)."""
     device = default_device()
+    # Device-resident chunks that need no copy or conversion are prepared ONCE per (array, labels) pair: the views, the
+    # C-ABI chunk table and the offsets are reused by every later call (a map-reduce loop over the same dask-like
+    # collection).  Chunk CONTENTS may change between calls, the tensors themselves must not be swapped.
+    world = ctx.comm.world_size if ctx.comm.enabled else 1
+    key = (id(by), ctx.sharding, ctx.comm.rank if ctx.comm.enabled else 0, world, str(device))
+    cached = getattr(array, "_prepared", None)
+    if cached is not None and not need_global_index and cached[0] == key and cached[1] is by:
+        return cached[2]
+    copied = False
     mine = ctx.my_chunks(array.nchunks)
     sizes = array.chunk_sizes
     start = 0
@@ -172,6 +181,7 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     for k in mine:  # all value copies are enqueued first: the link is busy while the worker threads pack labels
         v = array.chunks[k]
         if not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
+            copied = True
             v = to_device(v, device)
             if v.dtype != kdt:
                 v = v.to(kdt)
@@ -181,12 +191,19 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
         v = values[k]
         c = packed.get(k, labels[k])
         if not (is_torch(c) and c.device == device and c.dtype in _CODE_DTYPES and c.is_contiguous()):
+            copied = True
             c = to_device(c, device)
             if c.dtype not in _CODE_DTYPES:
                 c = c.to(torch.int64)
         chunks.append((v.view(A, -1, 1), c.view(-1)))
         index_base.append(int(offsets[k]) + start)
-    return chunks, index_base, lead, A, kdt, device
+    out = (PreparedChunks(chunks), index_base, lead, A, kdt, device)
+    if not copied and not packed and not need_global_index:
+        try:
+            array._prepared = (key, by, out)
+        except AttributeError:
+            pass
+    return out
 
 
 def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_groups: pd.RangeIndex, axis, fill_value,
@@ -207,7 +224,14 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
     def typed(t, dt):
         return from_device(t.reshape(shape), like, dt)
 
-    if method == "map-reduce" and not _is_arg_reduction(agg):
+    if (method == "map-reduce" and agg.name in ("mean", "nanmean") and agg.min_count == 0 and len(agg.chunk) == 2
+            and np.dtype(agg.dtype["final"]).kind == "f"):
+        # mean = sum / count (aggregations.py:323-336): ONE epilogue launch does what the reference's finalize does with
+        # the two combined intermediates — the sum rounded to its intermediate dtype, divided in f64, rounded to the
+        # final dtype; absent groups are 0 / 0 = NaN like the reference's reindexed intermediates
+        funcs, fills, dts = (agg.name,), (0,), (agg.dtype["final"],)
+        do_finalize = False
+    elif method == "map-reduce" and not _is_arg_reduction(agg):
         funcs, fills, dts = agg.chunk, agg.fill_value["intermediate"], agg.dtype["intermediate"]
         do_finalize = True
     else:  # blockwise / cohorts / arg-reductions: straight to the numpy-path value

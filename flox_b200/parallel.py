@@ -57,6 +57,15 @@ class Comm:
     def prod_(self, t):
         return self._reduce(t, dist.ReduceOp.PRODUCT)
 
+    def peer(self, nbytes: int, device: torch.device):
+        """The one-launch NVLink peer-memory exchange for an accumulator set of `nbytes`, or None (-> NCCL): see
+        flox_b200/exchange.py.  Every rank must ask with the same `nbytes` in the same order."""
+        if not self.enabled:
+            return None
+        from .exchange import peer_exchange
+
+        return peer_exchange(self.group, nbytes, device)
+
     def all_gather_object(self, obj):
         if not self.enabled:
             return [obj]

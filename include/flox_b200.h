@@ -210,6 +210,41 @@ int floxb_lut_codes(const void* labels, int label_dtype, int64_t n, int64_t lo, 
 int floxb_host_pack_codes(const void* codes, int code_dtype, int64_t n, int64_t n_groups, void* out, int out_bits);
 int floxb_widen_codes(const int16_t* codes16, int64_t n, int32_t* codes32, void* stream);
 
+/* ---- cross-GPU combine over NVLink peer memory (one box, one process per GPU) ---------------------------------------
+ * Replaces the exchange step of flox's map-reduce — `_tree_reduce(combine=_simple_combine)`, flox/dask.py:440-460 with
+ * flox/dask_array_ops.py:29-121 — for accumulator sets small enough to be latency-bound (NCCL remains the path for
+ * large ones, flox_b200/parallel.py).  Every rank owns a SLAB:
+ *     [header: FLOXB_XCHG_HEADER_BYTES][buffer 0][buffer 1]        (the caller double-buffers: collective s uses s % 2)
+ * allocated with floxb_ipc_alloc and mapped by every peer with floxb_ipc_open (CUDA IPC; handles travel through the
+ * host-side process group).  The reduction kernels accumulate straight into the slab; floxb_xchg_allreduce then runs a
+ * flag barrier over peer memory and merges word j of all `world` buffers in rank order (bit-identical results on every
+ * rank) into local `outs`.  Collectives must be issued in the same order with the same `epoch` (1, 2, 3, ...) on all ranks.
+ *   floxb_ipc_alloc   cudaMalloc + zero + export: *dptr = slab, handle64 = 64-byte cudaIpcMemHandle_t (HOST memory)
+ *   floxb_ipc_open    map a peer's handle (peer access is enabled lazily); floxb_ipc_close / floxb_ipc_free undo both
+ *   floxb_xchg_allreduce
+ *       slab_bases   HOST array of `world` device pointers: this process's mapping of every rank's slab (own at [rank])
+ *       data_offset  byte offset of the buffer in use inside each slab (>= FLOXB_XCHG_HEADER_BYTES, multiple of 8)
+ *       seg_words / seg_ops / outs   HOST arrays, n_segments <= FLOXB_XCHG_MAX_SEGMENTS: consecutive runs of 8-byte
+ *                    words in the buffer, how to combine each (FLOXB_XCHG_*), and the local device destination of each
+ *   floxb_xchg_status *failed_epoch != 0: a barrier gave up waiting (~2 s) for a peer in that collective (the results
+ *                    of it and everything after are undefined).  Synchronises the device. */
+#define FLOXB_XCHG_MAX_RANKS 8
+#define FLOXB_XCHG_MAX_SEGMENTS 4
+#define FLOXB_XCHG_HEADER_BYTES 128
+#define FLOXB_XCHG_SUM_F64 0
+#define FLOXB_XCHG_SUM_I64 1
+#define FLOXB_XCHG_MAX_I64 2
+#define FLOXB_XCHG_MIN_I64 3
+#define FLOXB_XCHG_PROD_F64 4
+#define FLOXB_XCHG_PROD_I64 5
+int floxb_ipc_alloc(int64_t bytes, void** dptr, void* handle64);
+int floxb_ipc_open(const void* handle64, void** dptr);
+int floxb_ipc_close(void* dptr);
+int floxb_ipc_free(void* dptr);
+int floxb_xchg_allreduce(void* const* slab_bases, int world, int rank, uint64_t epoch, int64_t data_offset,
+                         int n_segments, const int64_t* seg_words, const int* seg_ops, void* const* outs, void* stream);
+int floxb_xchg_status(const void* slab_base, uint64_t* failed_epoch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,7 @@ ncucols)
 dist)
   NG=$(nvidia-smi -L | wc -l)
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
-      tools/dist_check.py > gpurun_out/dist_check.log 2>&1; echo "dist_check rc=$?" >> gpurun_out/dist_check.log
+      tests/dist_worker.py > gpurun_out/dist_check.log 2>&1; echo "dist_worker rc=$?" >> gpurun_out/dist_check.log
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
       bench.py --gpus $NG --steps 10 --warmup 3 > gpurun_out/bench_multi.log 2>&1; echo "bench_multi rc=$?" >> gpurun_out/bench_multi.log ;;
 esac
