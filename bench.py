@@ -350,6 +350,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = parallel.bind_to_gpu_numa(local)  # before any pinned allocation: staging buffers land on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     k = kernels.get_kernels()
@@ -570,7 +571,7 @@ def run_gpu(args):
         e2e = {"value": world * e2e_rows_local / dt, "unit": UNIT, "h2d_bytes_per_step": world * h2d,
                "d2h_bytes_per_step": world * int(out.numel() * out.element_size()), "ms_per_step": dt * 1e3,
                "steps": args.e2e_steps, "host_bytes_per_step": world * e2e_rows_local * BYTES_PER_ROW,
-               "rows_per_gpu": e2e_rows_local,
+               "rows_per_gpu": e2e_rows_local, "numa_local_cpus": (len(numa_cpus) if numa_cpus else None),
                "how": "pinned host chunks (f32 values + int64 labels) -> groupby_reduce(ChunkedArray, method='map-reduce') -> host "
                       "result; labels are range-checked and narrowed to int16 by host threads on the way to the pinned staging "
                       "buffers when that pays (see flox_b200/mapreduce.py:_stage_packed_codes)"}

@@ -353,28 +353,42 @@ k_moments_smem_fx(const __grid_constant__ ChunkTable tab, int G, double* __restr
       slow_row(v, (int)c);
     }
   };
-  // the four rows of a tile in phases, so that four returning atomics are in flight per thread instead of one
+  // The four rows of a tile.  ncu on the first version of this kernel: 84% of the issue slots busy, 68 instructions per
+  // row — the kernel had become ISSUE-bound (generic->shared address conversion in front of every atomic, a
+  // BSSY/BRA/BSYNC triple around each, predicates spilled into a mask register).  So: when all 128 rows of the warp
+  // are ordinary (valid code, value inside the exact window — practically always), a straight-line path issues the
+  // eight native atomics through 32-bit shared-memory addresses with no branch in between; anything else takes the
+  // row-by-row path above.
+  const unsigned slo_s = (unsigned)__cvta_generic_to_shared(slo);
+  const unsigned hi_off = (unsigned)S * 4u;
+  const unsigned copy4 = (unsigned)copy * 4u;
+  auto atoms_add = [](unsigned addr, unsigned v) -> unsigned {
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+  };
   auto add_tile = [&](const Vec4<float>& v, const Vec4<CT>& c) {
-    unsigned lo[4], hi[4], old[4], oh[4];
-    int st[4], sl[4];
+    unsigned lo[4], hi[4];
+    bool all_fast = true;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      st[k] = convert(v.v[k], c.v[k], lo[k], hi[k]);
-      sl[k] = ((int)c.v[k] << RSHIFT) | copy;
-    }
+    for (int k = 0; k < 4; ++k) all_fast &= convert(v.v[k], c.v[k], lo[k], hi[k]) == 1;
+    if (__all_sync(0xffffffffu, all_fast)) {
+      unsigned la[4], old[4], oh[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (st[k] == 1) old[k] = atomicAdd(&slo[sl[k]], lo[k]);
+      for (int k = 0; k < 4; ++k) la[k] = slo_s + ((unsigned)c.v[k] << (2 + RSHIFT)) + copy4;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (st[k] == 1) oh[k] = atomicAdd(&shi[sl[k]], (1u << kFxCountShift) + hi[k] + (unsigned)((old[k] + lo[k]) < lo[k]));
+      for (int k = 0; k < 4; ++k) old[k] = atoms_add(la[k], lo[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (st[k] == 1) {
-        if ((oh[k] >> kFxCountShift) >= kFxDrain - 1) drain(sl[k]);
-      } else if (st[k] == 2) {
-        slow_row(v.v[k], (int)c.v[k]);
+      for (int k = 0; k < 4; ++k)
+        oh[k] = atoms_add(la[k] + hi_off, (1u << kFxCountShift) + hi[k] + (unsigned)((old[k] + lo[k]) < lo[k]));
+      if ((oh[0] | oh[1] | oh[2] | oh[3]) >= ((kFxDrain - 1) << kFxCountShift)) {  // rare: some slot may be full
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if ((oh[k] >> kFxCountShift) >= kFxDrain - 1) drain(((int)c.v[k] << RSHIFT) | copy);
       }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add_row(v.v[k], c.v[k]);
     }
   };
 

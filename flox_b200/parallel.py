@@ -77,6 +77,39 @@ class Comm:
 LOCAL = Comm(enabled=False)
 
 
+def bind_to_gpu_numa(device_index: int | None = None) -> list[int] | None:
+    """Pin this process (and the label-pack worker threads it will start) to the CPU cores that are NUMA-local to its
+    GPU, so that pinned staging buffers are first-touched on that node and host->device copies do not cross the
+    socket interconnect.  One process per GPU on a two-socket box otherwise lands its buffers wherever the launcher
+    happened to run it: round 1 measured 28 GB/s per GPU at 8 GPUs, half of what one GPU gets alone.
+    Call it BEFORE allocating pinned memory.  Returns the CPU list, or None if NVML / affinity are unavailable
+    (FLOXB_NUMA=0 disables it)."""
+    import os
+
+    if os.environ.get("FLOXB_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and idx < len(vis.split(",")):
+            idx = int(vis.split(",")[idx])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = {w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001 - no NVML, no permission, exotic topology: stay unpinned
+        return None
+
+
 @dataclass
 class ParallelContext:
     """How chunked inputs map onto ranks.
