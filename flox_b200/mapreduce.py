@@ -178,9 +178,20 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     chunks, index_base = [], []
     labels = {k: (by_chunks[k] if by_chunks is not None else by[..., int(offsets[k]):int(offsets[k]) + sizes[k]]) for k in mine}
     values = {}
+    # Slabs whose reduced (last) axis is OUTERMOST in memory — a (rows, columns) block handed over as block.T, which is
+    # what moving the grouped dim to the end gives (flox/core.py:1014-1018) — are consumed in place as values[1, n, B]
+    # (B = the kept columns: BASELINE config 4's layout), like the in-memory path does (aggregate_b200.make_accumulators).
+    time_major = bool(lead) and all(
+        is_torch(array.chunks[k]) and array.chunks[k].device == device and array.chunks[k].dtype == kdt
+        and not array.chunks[k].is_contiguous() and array.chunks[k].movedim(-1, 0).is_contiguous() for k in mine)
+    B = A if time_major else 1
+    if time_major:
+        A = 1
     for k in mine:  # all value copies are enqueued first: the link is busy while the worker threads pack labels
         v = array.chunks[k]
-        if not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
+        if time_major:
+            v = v.movedim(-1, 0)
+        elif not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
             copied = True
             v = to_device(v, device)
             if v.dtype != kdt:
@@ -195,9 +206,9 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
             c = to_device(c, device)
             if c.dtype not in _CODE_DTYPES:
                 c = c.to(torch.int64)
-        chunks.append((v.view(A, -1, 1), c.view(-1)))
+        chunks.append((v.reshape(1, -1, B) if time_major else v.view(A, -1, 1), c.view(-1)))
         index_base.append(int(offsets[k]) + start)
-    out = (PreparedChunks(chunks), index_base, lead, A, kdt, device)
+    out = (PreparedChunks(chunks), index_base, lead, (A, B), kdt, device)
     if not copied and not packed and not need_global_index:
         try:
             array._prepared = (key, by, out)
@@ -214,9 +225,9 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
         raise NotImplementedError("chunked inputs are grouped by 1-D labels along the chunked (last) axis")
     ctx = parallel.current()
     G = len(expected_groups)
-    chunks, index_base, lead, A, kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg),
-                                                                    n_groups=G)
-    acc = GroupedAccumulators(chunks, A, 1, G, kdt, device, index_base=index_base, comm=ctx.comm)
+    chunks, index_base, lead, (A, B), kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg),
+                                                                         n_groups=G)
+    acc = GroupedAccumulators(chunks, A, B, G, kdt, device, index_base=index_base, comm=ctx.comm)
     like = array.chunks[0]
     array_np_dtype = array.dtype
     shape = lead + (G,)
