@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -88,11 +89,16 @@ _VALUE_DTYPES = (torch.float32, torch.float64, torch.int32, torch.int64)
 
 
 _pack_pool: ThreadPoolExecutor | None = None
+_pack_pool_lock = threading.Lock()
 
 
 def _pool(world: int) -> ThreadPoolExecutor:
     global _pack_pool
-    if _pack_pool is None:
+    if _pack_pool is not None:
+        return _pack_pool
+    with _pack_pool_lock:  # concurrent first calls (dask threads) must end up sharing ONE pool
+        if _pack_pool is not None:
+            return _pack_pool
         # the pack is bound by host memory bandwidth: on the B200 box 16 threads are the optimum (107 ms per 8 GB of
         # int64 labels; 32 threads 131 ms, 128 threads 307 ms — tools/e2e_probe.py)
         want = int(os.environ.get("FLOXB_PACK_THREADS", "16"))

@@ -14,6 +14,7 @@ code runs single-GPU.
 from __future__ import annotations
 
 import contextlib
+import contextvars
 from dataclasses import dataclass
 
 import torch
@@ -132,22 +133,25 @@ class ParallelContext:
         return range(lo, lo + base + (1 if r < extra else 0))
 
 
-_current = ParallelContext()
+# The active context is per THREAD (and per asyncio task): dask's threaded scheduler calls the per-chunk driver from many
+# threads at once (the reference's race regression: tests/test_core.py:1827-1851), and one thread entering
+# `distributed()` must not switch another thread's calls to multi-rank mode.
+_DEFAULT = ParallelContext()
+_current: contextvars.ContextVar = contextvars.ContextVar("flox_b200_parallel_context", default=_DEFAULT)
 
 
 def current() -> ParallelContext:
-    return _current
+    return _current.get()
 
 
 @contextlib.contextmanager
 def distributed(group=None, sharding: str = "replicated"):
     """Run `groupby_reduce` on ChunkedArrays across the ranks of `group` (default: WORLD)."""
-    global _current
     if sharding not in ("replicated", "local"):
         raise ValueError("sharding must be 'replicated' or 'local'")
-    prev = _current
-    _current = ParallelContext(Comm(group), sharding)
+    ctx = ParallelContext(Comm(group), sharding)
+    token = _current.set(ctx)
     try:
-        yield _current
+        yield ctx
     finally:
-        _current = prev
+        _current.reset(token)

@@ -188,3 +188,29 @@ def test_in_memory_labels_next_to_chunked_ones(emu):  # noqa: F811
                                        expected_groups=(np.arange(3), np.arange(4)), method="map-reduce")
     want, *_ = flox_b200.groupby_reduce(x, b0, b1, func="sum", expected_groups=(np.arange(3), np.arange(4)))
     np.testing.assert_allclose(np.asarray(got), np.nan_to_num(want), rtol=1e-12)
+
+
+def test_parallel_context_is_per_thread():
+    """`parallel.distributed()` entered by one thread must not change what other threads see (dask's threaded
+    scheduler runs chunk tasks concurrently; the reference's race regression is tests/test_core.py:1827-1851)."""
+    import threading
+
+    from flox_b200 import parallel
+
+    seen = {}
+    inside, release = threading.Event(), threading.Event()
+
+    def holder():
+        with parallel.distributed(sharding="local") as ctx:
+            seen["holder"] = parallel.current() is ctx and parallel.current().sharding == "local"
+            inside.set()
+            release.wait(10)
+
+    t = threading.Thread(target=holder)
+    t.start()
+    assert inside.wait(10)
+    seen["other"] = parallel.current().sharding
+    release.set()
+    t.join()
+    assert seen["holder"] and seen["other"] == "replicated"
+    assert parallel.current().sharding == "replicated"
