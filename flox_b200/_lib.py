@@ -54,6 +54,8 @@ SIGNATURES = {
     "floxb_lut_codes": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "floxb_host_pack_codes": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32]),
     "floxb_widen_codes": (_i32, [_vp, _i64, _vp, _vp]),
+    "floxb_segment_valid": (_i32, [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "floxb_segment_quantile": (_i32, [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _f64, _i32, _vp, _vp]),
     "floxb_ipc_alloc": (_i32, [_i64, C.POINTER(_vp), _vp]),
     "floxb_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
     "floxb_ipc_close": (_i32, [_vp]),

@@ -30,6 +30,7 @@ from .reductions import evaluate
 __all__ = [
     "sum", "nansum", "prod", "nanprod", "max", "nanmax", "min", "nanmin", "nanlen", "mean", "nanmean",
     "sum_of_squares", "nansum_of_squares", "argmax", "argmin", "nanargmax", "nanargmin", "var", "nanvar", "std", "nanstd",
+    "quantile", "nanquantile", "median", "nanmedian",
 ]
 
 
@@ -123,3 +124,81 @@ argmax = _engine("argmax", fixed_dtype=np.int64)
 argmin = _engine("argmin", fixed_dtype=np.int64)
 nanargmax = _engine("nanargmax", fixed_dtype=np.int64)
 nanargmin = _engine("nanargmin", fixed_dtype=np.int64)
+
+
+# ---- sorted-segment family: quantile / median ---------------------------------------------------
+
+def _sort_rows_by_group_then_value(vals: torch.Tensor, codes: torch.Tensor, size: int) -> torch.Tensor:
+    """Every row of `vals[R, n]` ordered by (code, value), NaNs last within their group, rows without a group (code
+    outside [0, size)) behind everything — the order the reference reaches by partitioning `code + 1j * value`
+    (flox/aggregate_flox.py:100-113).  f32: ONE 64-bit radix sort of the composite key (code << 32 | order-preserving value
+    bits); f64: a stable sort by value followed by a stable sort by code (the device radix sorts behind torch.sort)."""
+    codes = torch.where((codes >= 0) & (codes < size), codes, torch.full_like(codes, size))
+    if vals.dtype == torch.float32:
+        bits = vals.contiguous().view(torch.int32)
+        key = bits ^ ((bits >> 31) & 0x7FFFFFFF)                       # signed order == numeric order
+        key = torch.where(torch.isnan(vals), torch.full_like(key, 0x7FFFFFFF), key)
+        comp = (codes.to(torch.int64) << 32)[None, :] + (key.to(torch.int64) + (1 << 31))
+        comp = torch.sort(comp, dim=-1).values
+        key = ((comp & 0xFFFFFFFF) - (1 << 31)).to(torch.int32)
+        return (key ^ ((key >> 31) & 0x7FFFFFFF)).view(torch.float32)
+    by_value = torch.sort(vals, dim=-1, stable=True)                   # NaN sorts last
+    order = torch.sort(codes[by_value.indices], dim=-1, stable=True).indices
+    return torch.gather(by_value.values, -1, order)
+
+
+def _quantile_engine(func: str, skipna: bool, fixed_q=None):
+    def kernel(group_idx, array, *, q=fixed_q, axis=-1, size=None, fill_value=None, dtype=None, **kwargs):
+        if q is None:
+            raise ValueError(f"{func} needs q")
+        if axis not in (-1, np.ndim(array) - 1):
+            raise ValueError("the b200 engine reduces along the last axis (as chunk_reduce always asks)")
+        from .kernels import get_kernels
+
+        device = default_device()
+        np_dt = np_dtype_of(array)
+        if np_dt.kind in "Mm":
+            raise NotImplementedError("quantiles of datetime / timedelta arrays are not implemented by the b200 engine")
+        vals = to_device(array, device)
+        if vals.dtype not in (torch.float32, torch.float64):
+            vals = vals.to(torch.float64)                              # integers: exact below 2^53, like the reference's float64 view
+        codes = _codes_to_device(group_idx, device).to(torch.int64)
+        n = codes.numel()
+        if vals.ndim == 0 or vals.shape[-1] != n:
+            raise ValueError("array.shape[-1] must equal len(group_idx)")
+        if size is None:
+            size = int(codes.max().item()) + 1 if n else 0
+        size = int(size)
+        lead = tuple(vals.shape[:-1])
+        R = math.prod(lead)
+        qs = np.atleast_1d(np.asarray(q, dtype=np.float64))
+        out_dt = np.dtype(dtype) if dtype is not None else (np_dt if np_dt.kind == "f" else np.dtype("float64"))
+        kdt = torch.float32 if out_dt == np.dtype("float32") else torch.float64
+        fill = float("nan") if fill_value is None else float(fill_value)
+        out = torch.empty((len(qs), R, size), dtype=kdt, device=device)
+        if n == 0 or R == 0 or size == 0:
+            out.fill_(fill)
+        else:
+            k = get_kernels()
+            srt = _sort_rows_by_group_then_value(vals.reshape(R, n), codes, size).contiguous()
+            counts = torch.bincount(codes[(codes >= 0) & (codes < size)], minlength=size)
+            starts = torch.zeros(size + 1, dtype=torch.int64, device=device)
+            starts[1:] = torch.cumsum(counts, 0)
+            nvalid = torch.empty((R, size), dtype=torch.int64, device=device)
+            k.segment_valid(srt, starts, nvalid)
+            before = torch.cumsum(nvalid, dim=1) - nvalid               # valid values of the row's earlier groups
+            k.segment_quantile(srt, starts, nvalid, before.contiguous(), torch.as_tensor(qs, device=device), skipna, fill, out)
+        res = out.reshape((len(qs),) + lead + (size,))
+        return from_device(res, array, out_dt)
+
+    kernel.__name__ = func
+    kernel.__qualname__ = func
+    kernel.__doc__ = (f"Grouped `{func}` on the GPU (flox/aggregate_flox.py:50-130,218-221): result `(nq,) + array.shape[:-1] + "
+                      "(size,)`, bit-identical to the reference's.")
+    return kernel
+
+
+quantile = _quantile_engine("quantile", False)
+nanquantile = _quantile_engine("nanquantile", True)
+median = _quantile_engine("median", False, fixed_q=0.5)
+nanmedian = _quantile_engine("nanmedian", True, fixed_q=0.5)

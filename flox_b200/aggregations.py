@@ -52,6 +52,28 @@ def _atleast_1d(inp, min_length: int = 1):
     return tuple(inp)
 
 
+class Dim:
+    """A dimension a reduction adds to its result (aggregations.py:148-158): the quantile axis."""
+
+    def __init__(self, name, values):
+        self.name, self.values = name, values
+
+    @property
+    def is_scalar(self) -> bool:
+        return is_scalar(self.values)
+
+    @property
+    def size(self) -> int:
+        return 0 if self.is_scalar else len(self.values)
+
+
+def quantile_new_dims_func(q) -> tuple:
+    return (Dim(name="quantile", values=q),)
+
+
+QUANTILE_FUNCS = ("quantile", "nanquantile", "median", "nanmedian")
+
+
 class Aggregation:
     """Blueprint of a grouped reduction: per-chunk funcs, combine funcs, finalize, fills, dtypes.
 
@@ -195,6 +217,14 @@ def _build_reductions() -> dict[str, Aggregation]:
         "min": A("min", chunk="min", combine="min", fill_value=INF, preserves_dtype=True),
         "nanmin": A("nanmin", chunk="nanmin", combine="nanmin", fill_value=INF, final_fill_value=NA, preserves_dtype=True),
     }
+    # sorted-segment family: only in-memory / blockwise (aggregations.py:672-712: "Support statistical quantities only
+    # blockwise")
+    table["median"] = A("median", chunk=None, combine=None, fill_value=NA, final_dtype=np.floating)
+    table["nanmedian"] = A("nanmedian", chunk=None, combine=None, fill_value=NA, final_dtype=np.floating)
+    table["quantile"] = A("quantile", chunk=None, combine=None, fill_value=NA, final_dtype=np.float64,
+                          new_dims_func=quantile_new_dims_func)
+    table["nanquantile"] = A("nanquantile", chunk=None, combine=None, fill_value=NA, final_dtype=np.float64,
+                             new_dims_func=quantile_new_dims_func)
     for name, skipna, std in (("var", False, False), ("nanvar", True, False), ("std", False, True), ("nanstd", True, True)):
         table[name] = A(
             name, chunk=partial(var_chunk, skipna=skipna),

@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJDIR = os.path.join(PKG, "csrc", "build")
 LIB = os.path.join(PKG, "libflox_b200.so")
-SOURCES = ["moments.cu", "minmax.cu", "pass2.cu", "finalize.cu", "cols.cu", "staging.cu", "exchange.cu"]
+SOURCES = ["moments.cu", "minmax.cu", "pass2.cu", "finalize.cu", "cols.cu", "staging.cu", "exchange.cu", "segments.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math=false",

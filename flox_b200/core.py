@@ -29,8 +29,8 @@ import torch
 from . import xrdtypes
 from .aggregate_b200 import make_accumulators
 from .aggregations import (
-    ENGINES, Aggregation, _atleast_1d, _initialize_aggregation, _is_arg_reduction, blockwise_or_numpy_var,
-    is_var_chunk_reduction, var_chunk,
+    ENGINES, QUANTILE_FUNCS, Aggregation, _atleast_1d, _initialize_aggregation, _is_arg_reduction, blockwise_or_numpy_var,
+    is_var_chunk_reduction, quantile_new_dims_func, var_chunk,
 )
 from .arrays import from_device, is_torch, np_dtype_of
 from .factorize import _factorize_multiple, factorize_
@@ -171,7 +171,8 @@ def chunk_reduce(array, by, func, expected_groups, axis=None, fill_value=None, d
         elif _is_nanlen(reduction) and _is_nanlen(previous):
             result = results["intermediates"][-1]
         else:
-            if (is_var or not callable(reduction)) and acc is None:
+            is_quantile = isinstance(reduction, str) and reduction in QUANTILE_FUNCS
+            if (is_var or not (callable(reduction) or is_quantile)) and acc is None:
                 acc, lead, size = make_accumulators(group_idx, array2, size)
             if is_var:
                 base, pkw = (reduction.func, reduction.keywords) if isinstance(reduction, partial) else (reduction, {})
@@ -186,6 +187,17 @@ def chunk_reduce(array, by, func, expected_groups, axis=None, fill_value=None, d
                     ddof = kw.get("ddof", pkw.get("ddof", 0))
                     t = evaluate(acc, name, out_dtype=out_dt, fill_value=np.nan, ddof=ddof)
                     result = from_device(t.reshape(lead + (size,)), array, out_dt).reshape(out_shape)
+            elif isinstance(reduction, str) and reduction in QUANTILE_FUNCS:
+                # sorted-segment family: one sort of the chunk by (group, value), then per-group order statistics
+                from . import aggregate_b200
+
+                out_dt = np.dtype(dt) if dt is not None else (array_np_dtype if array_np_dtype.kind == "f" else np.dtype("float64"))
+                result = getattr(aggregate_b200, reduction)(group_idx, array2, size=size, dtype=out_dt, fill_value=fv, **kw)
+                if reduction in ("quantile", "nanquantile"):  # core.py:385-389
+                    new_dims_shape = tuple(d.size for d in quantile_new_dims_func(**kw) if not d.is_scalar)
+                else:
+                    new_dims_shape = ()
+                result = result.reshape(new_dims_shape + out_shape)
             elif callable(reduction):
                 # custom Aggregation chunk function: it does its own grouped reduction (core.py:360-366)
                 result = reduction(group_idx, array2, size=size, dtype=dt, fill_value=fv, **kw)
@@ -422,9 +434,10 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
 
     if engine is not None and engine not in ENGINES:
         raise ValueError(f"Expected engine to be one of {list(ENGINES)}. Received {engine} instead.")
-    if func in ("quantile", "nanquantile", "median", "nanmedian", "mode", "nanmode", "first", "last", "nanfirst",
-                "nanlast", "all", "any"):
-        raise NotImplementedError(f"Reduction {func!r} is outside the b200 engine's scatter-reduction scope")
+    if func in ("mode", "nanmode", "first", "last", "nanfirst", "nanlast", "all", "any"):
+        raise NotImplementedError(f"Reduction {func!r} is outside the b200 engine's scope")
+    if func in ("quantile", "nanquantile") and (finalize_kwargs is None or "q" not in finalize_kwargs):
+        raise ValueError("Please pass `q` for quantile calculations.")  # core.py:869-871
 
     bys = tuple(b if (is_torch(b) or is_chunked(b)) else np.asarray(b) for b in by)
     nby = len(bys)
@@ -525,6 +538,9 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
 
         if nax != by_.ndim:
             raise NotImplementedError("Chunked arrays must be reduced along all dimensions of `by`.")
+        if func in QUANTILE_FUNCS:
+            raise NotImplementedError(f"{func!r} needs every group in one block: concatenate the chunks (the reference "
+                                      "supports it for method='blockwise' only, aggregations.py:672-673)")
         method = method or "map-reduce"
         if method not in ("map-reduce", "blockwise", "cohorts"):
             raise ValueError(f"Unknown method {method!r}")

@@ -287,6 +287,25 @@ class CudaKernels:
         self.launches += 1
         self.kernel_launches += 1 if labels.numel() else 0
 
+    # -- sorted-segment family (csrc/segments.cu) ----------------------------------------------------
+    def segment_valid(self, sorted_vals, starts, nvalid):
+        self._require_cuda(sorted_vals, starts, nvalid)
+        R, n = sorted_vals.shape
+        L.check(L.load().floxb_segment_valid(self._ptr(sorted_vals), dtype_code(sorted_vals.dtype), R, n, self._ptr(starts),
+                                             starts.numel() - 1, self._ptr(nvalid), self._stream()), "floxb_segment_valid")
+        self.launches += 1
+        self.kernel_launches += 1 if nvalid.numel() else 0
+
+    def segment_quantile(self, sorted_vals, starts, nvalid, before, q, skipna: bool, fill: float, out):
+        self._require_cuda(sorted_vals, starts, nvalid, before, q, out)
+        R, n = sorted_vals.shape
+        L.check(L.load().floxb_segment_quantile(self._ptr(sorted_vals), dtype_code(sorted_vals.dtype), R, n, self._ptr(starts),
+                                                starts.numel() - 1, self._ptr(nvalid), self._ptr(before), self._ptr(q),
+                                                q.numel(), int(skipna), float(fill), dtype_code(out.dtype), self._ptr(out),
+                                                self._stream()), "floxb_segment_quantile")
+        self.launches += 1
+        self.kernel_launches += 1 if out.numel() else 0
+
     def smem_group_limit(self, value_dtype, family: int) -> int:
         return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))
 

@@ -210,6 +210,23 @@ int floxb_lut_codes(const void* labels, int label_dtype, int64_t n, int64_t lo, 
 int floxb_host_pack_codes(const void* codes, int code_dtype, int64_t n, int64_t n_groups, void* out, int out_bits);
 int floxb_widen_codes(const int16_t* codes16, int64_t n, int32_t* codes32, void* stream);
 
+/* ---- sorted-segment family: grouped quantile / median ----------------------------------------
+ * Replaces aggregate_flox.quantile_ (flox/aggregate_flox.py:50-130) behind quantile / nanquantile / median / nanmedian
+ * (:218-221).  The caller sorts every row by (group, value), NaNs last within their group (the reference partitions a
+ * complex array group + 1j * value for the same order, :100-113), and passes
+ *   sorted   [n_rows, n] values (F32 / F64)                  starts   i64[n_groups + 1]: segment of group g in every row
+ *   floxb_segment_valid     nvalid[n_rows, n_groups] = non-NaN values per (row, group)
+ *   floxb_segment_quantile  out[n_q, n_rows, n_groups]: numpy's method="linear" quantile of the valid values, NaN for a
+ *                           group without valid values (or, skipna = 0, holding a NaN), `fill` for a group that does not
+ *                           occur.  before[n_rows, n_groups] = exclusive running sum of nvalid along the groups of a row:
+ *                           the reference's virtual index is formed on the row's compacted valid values and this offset
+ *                           decides the last bits of the interpolation weight (:85-90); results are bit-identical. */
+int floxb_segment_valid(const void* sorted, int value_dtype, int64_t n_rows, int64_t n, const int64_t* starts,
+                        int64_t n_groups, int64_t* nvalid, void* stream);
+int floxb_segment_quantile(const void* sorted, int value_dtype, int64_t n_rows, int64_t n, const int64_t* starts,
+                           int64_t n_groups, const int64_t* nvalid, const int64_t* before, const double* q, int n_q,
+                           int skipna, double fill, int out_dtype, void* out, void* stream);
+
 /* ---- cross-GPU combine over NVLink peer memory (one box, one process per GPU) ---------------------------------------
  * Replaces the exchange step of flox's map-reduce — `_tree_reduce(combine=_simple_combine)`, flox/dask.py:440-460 with
  * flox/dask_array_ops.py:29-121 — for accumulator sets small enough to be latency-bound (NCCL remains the path for

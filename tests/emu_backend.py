@@ -324,3 +324,40 @@ class EmuKernels:
 
     def widen_codes(self, codes16):
         return codes16.to(torch.int32)
+
+    # -- sorted-segment family (csrc/segments.cu) ----------------------------------------------------
+    def segment_valid(self, sorted_vals, starts, nvalid):
+        self.launches += 1
+        v, s = _np(sorted_vals), _np(starts)
+        out = _np(nvalid).reshape(v.shape[0], len(s) - 1)
+        for g in range(len(s) - 1):
+            out[:, g] = (~np.isnan(v[:, s[g]:s[g + 1]])).sum(axis=1)
+
+    def segment_quantile(self, sorted_vals, starts, nvalid, before, q, skipna, fill, out):
+        self.launches += 1
+        v, s, qs = _np(sorted_vals), _np(starts), _np(q)
+        R, G = v.shape[0], len(s) - 1
+        nv, bef = _np(nvalid).reshape(R, G), _np(before).reshape(R, G)
+        o = _np(out).reshape(len(qs), R, G)
+        rows = np.arange(R)
+        with np.errstate(all="ignore"):
+            for g in range(G):
+                ln = s[g + 1] - s[g]
+                for iq, qq in enumerate(qs):
+                    if ln == 0:
+                        o[iq, :, g] = fill
+                        continue
+                    virt = qq * (nv[:, g] - 1).astype(np.float64)
+                    virt = np.where(bef[:, g] != 0, virt + bef[:, g].astype(np.float64), virt)
+                    fl, ce = np.floor(virt), np.ceil(virt)
+                    gamma = virt - fl
+                    li = np.clip(fl.astype(np.int64) - bef[:, g], 0, ln - 1) + s[g]
+                    hi = np.clip(ce.astype(np.int64) - bef[:, g], 0, ln - 1) + s[g]
+                    a, b = v[rows, li], v[rows, hi]
+                    d = (b - a).astype(v.dtype)
+                    res = a.astype(np.float64) + d.astype(np.float64) * gamma
+                    res = np.where(gamma >= 0.5, b.astype(np.float64) - d.astype(np.float64) * (1.0 - gamma), res)
+                    bad = nv[:, g] == 0
+                    if not skipna:
+                        bad = bad | (nv[:, g] != ln)
+                    o[iq, :, g] = np.where(bad, np.nan, res).astype(o.dtype)

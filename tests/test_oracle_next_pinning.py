@@ -1,7 +1,7 @@
 """Pin the oracle of the NEXT rows (oracle/flox_oracle_next.py: grouped quantile / median and grouped scans,
 SURVEY §8f rank 4) to outputs of the UNMODIFIED reference (tests/golden/golden_next.*, written by
-tests/golden/make_golden_next.py).  Bit-exact, like tests/test_oracle_pinning.py.  The package itself does not
-implement these reductions yet and must say so."""
+tests/golden/make_golden_next.py).  Bit-exact, like tests/test_oracle_pinning.py.  The CUDA counterparts of the quantile family are
+tested in tests/test_next_rows_cpu.py / tests/test_gpu_next_rows.py; the scans have no kernels yet."""
 import json
 import os
 
@@ -45,7 +45,8 @@ def test_scans(case):
     assert_same(res, ARR[case["result"]], what=case["id"])
 
 
-@pytest.mark.parametrize("func", ["quantile", "nanmedian", "median"])
+@pytest.mark.parametrize("func", ["first", "nanlast", "mode"])
 def test_package_says_not_implemented(func):
+    """Reductions still outside the engine raise instead of falling back to a CPU engine."""
     with pytest.raises(NotImplementedError):
         flox_b200.groupby_reduce(np.ones(4), np.array([0, 0, 1, 1]), func=func)
