@@ -56,6 +56,8 @@ SIGNATURES = {
     "floxb_widen_codes": (_i32, [_vp, _i64, _vp, _vp]),
     "floxb_segment_valid": (_i32, [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp]),
     "floxb_segment_quantile": (_i32, [_vp, _i32, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _f64, _i32, _vp, _vp]),
+    "floxb_segment_scan_scratch_bytes": (_i64, [_i64, _i64]),
+    "floxb_segment_scan": (_i32, [_i32, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "floxb_ipc_alloc": (_i32, [_i64, C.POINTER(_vp), _vp]),
     "floxb_ipc_open": (_i32, [_vp, C.POINTER(_vp)]),
     "floxb_ipc_close": (_i32, [_vp]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "floxb_xchg_status": (_i32, [_vp, C.POINTER(C.c_uint64)]),
 }
 
+SCAN_CUMSUM, SCAN_FFILL = 0, 1
 XCHG_MAX_RANKS, XCHG_MAX_SEGMENTS, XCHG_HEADER_BYTES = 8, 4, 128
 XCHG_SUM_F64, XCHG_SUM_I64, XCHG_MAX_I64, XCHG_MIN_I64, XCHG_PROD_F64, XCHG_PROD_I64 = range(6)
 

@@ -30,7 +30,7 @@ from .reductions import evaluate
 __all__ = [
     "sum", "nansum", "prod", "nanprod", "max", "nanmax", "min", "nanmin", "nanlen", "mean", "nanmean",
     "sum_of_squares", "nansum_of_squares", "argmax", "argmin", "nanargmax", "nanargmin", "var", "nanvar", "std", "nanstd",
-    "quantile", "nanquantile", "median", "nanmedian",
+    "quantile", "nanquantile", "median", "nanmedian", "cumsum", "nancumsum", "ffill",
 ]
 
 
@@ -202,3 +202,50 @@ quantile = _quantile_engine("quantile", False)
 nanquantile = _quantile_engine("nanquantile", True)
 median = _quantile_engine("median", False, fixed_q=0.5)
 nanmedian = _quantile_engine("nanmedian", True, fixed_q=0.5)
+
+
+# ---- grouped scans: cumsum / nancumsum / ffill (flox/aggregate_flox.py:269-329) --------------------------------------------
+
+def _scan_engine(func: str, kind: int, skipna: bool):
+    def kernel(group_idx, array, *, axis=-1, dtype=None, **kwargs):
+        if axis not in (-1, np.ndim(array) - 1):
+            raise ValueError("the b200 engine scans along the last axis")
+        from .kernels import get_kernels
+
+        device = default_device()
+        np_dt = np_dtype_of(array)
+        if np_dt.kind in "Mm":
+            raise NotImplementedError("scans of datetime / timedelta arrays are not implemented by the b200 engine")
+        vals = to_device(array, device)
+        kdt = kernel_dtype(vals.dtype)
+        if kind == L.SCAN_CUMSUM and kdt == torch.int32:
+            kdt = torch.int64                                          # np.nancumsum widens small integers to the platform int
+        if vals.dtype != kdt:
+            vals = vals.to(kdt)
+        codes = _codes_to_device(group_idx, device).to(torch.int64)
+        n = codes.numel()
+        if vals.ndim == 0 or vals.shape[-1] != n:
+            raise ValueError("array.shape[-1] must equal len(group_idx)")
+        lead = tuple(vals.shape[:-1])
+        R = math.prod(lead)
+        out = torch.empty((R, n), dtype=kdt, device=device)
+        if R * n:
+            order = torch.sort(codes, stable=True)                     # labels only: the reference's _prepare_for_flox argsort
+            get_kernels().segment_scan(kind, vals.reshape(R, n).contiguous(), order.indices.contiguous(), order.values.contiguous(),
+                                       skipna, out)
+        out_np = _TORCH2NP_SCAN[kdt] if dtype is None else np.dtype(dtype)
+        return from_device(out.reshape(lead + (n,)), array, out_np)
+
+    kernel.__name__ = func
+    kernel.__qualname__ = func
+    kernel.__doc__ = f"Grouped `{func}` along the last axis, in order of appearance (flox/aggregate_flox.py:269-329)."
+    return kernel
+
+
+from . import _lib as L  # noqa: E402
+
+_TORCH2NP_SCAN = {torch.float32: np.dtype("float32"), torch.float64: np.dtype("float64"), torch.int32: np.dtype("int32"),
+                  torch.int64: np.dtype("int64")}
+cumsum = _scan_engine("cumsum", L.SCAN_CUMSUM, False)
+nancumsum = _scan_engine("nancumsum", L.SCAN_CUMSUM, True)
+ffill = _scan_engine("ffill", L.SCAN_FFILL, True)

@@ -306,6 +306,18 @@ class CudaKernels:
         self.launches += 1
         self.kernel_launches += 1 if out.numel() else 0
 
+    def segment_scan(self, kind: int, values, perm, sorted_codes, skipna: bool, out):
+        self._require_cuda(values, perm, sorted_codes, out)
+        R, n = values.shape
+        lib = L.load()
+        nbytes = int(lib.floxb_segment_scan_scratch_bytes(R, n))
+        scratch = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=values.device)
+        L.check(lib.floxb_segment_scan(kind, self._ptr(values), dtype_code(values.dtype), self._ptr(perm), self._ptr(sorted_codes),
+                                       R, n, int(skipna), self._ptr(scratch), nbytes, self._ptr(out), self._stream()),
+                "floxb_segment_scan")
+        self.launches += 1
+        self.kernel_launches += 3 if out.numel() else 0
+
     def smem_group_limit(self, value_dtype, family: int) -> int:
         return int(L.load().floxb_smem_group_limit(dtype_code(value_dtype), family))
 

@@ -227,6 +227,21 @@ int floxb_segment_quantile(const void* sorted, int value_dtype, int64_t n_rows, 
                            int64_t n_groups, const int64_t* nvalid, const int64_t* before, const double* q, int n_q,
                            int skipna, double fill, int out_dtype, void* out, void* stream);
 
+/* Grouped scans within groups, in order of appearance (flox/aggregate_flox.py:296-329 cumsum / nancumsum, :269-293 ffill).
+ *   values        [n_rows, n] in the ORIGINAL order (F32 / F64 / I32 / I64); out has the same shape, order and dtype
+ *   perm          i64[n]: stable argsort of the group codes (the reference's _prepare_for_flox permutation, labels only)
+ *   sorted_codes  i64[n]: codes[perm]
+ *   kind          FLOXB_SCAN_CUMSUM (skipna = 1: NaN counts as 0 = nancumsum; 0: a NaN poisons the rest of ITS group)
+ *                 or FLOXB_SCAN_FFILL (a NaN takes the last valid value before it within its group)
+ *   scratch       device memory of at least floxb_segment_scan_scratch_bytes(n_rows, n)
+ * A true segmented scan: sums accumulate in f64 / i64 per group and are rounded once (the reference subtracts the total that
+ * precedes the group from one global running sum, so its results carry that total's rounding). */
+#define FLOXB_SCAN_CUMSUM 0
+#define FLOXB_SCAN_FFILL 1
+int64_t floxb_segment_scan_scratch_bytes(int64_t n_rows, int64_t n);
+int floxb_segment_scan(int kind, const void* values, int value_dtype, const int64_t* perm, const int64_t* sorted_codes,
+                       int64_t n_rows, int64_t n, int skipna, void* scratch, int64_t scratch_bytes, void* out, void* stream);
+
 /* ---- cross-GPU combine over NVLink peer memory (one box, one process per GPU) ---------------------------------------
  * Replaces the exchange step of flox's map-reduce — `_tree_reduce(combine=_simple_combine)`, flox/dask.py:440-460 with
  * flox/dask_array_ops.py:29-121 — for accumulator sets small enough to be latency-bound (NCCL remains the path for

@@ -361,3 +361,32 @@ class EmuKernels:
                     if not skipna:
                         bad = bad | (nv[:, g] != ln)
                     o[iq, :, g] = np.where(bad, np.nan, res).astype(o.dtype)
+
+    def segment_scan(self, kind, values, perm, sorted_codes, skipna, out):
+        """A true segmented scan in f64 / i64 per group (what csrc/segments.cu does), rounded once."""
+        self.launches += 1
+        v, p, sc = _np(values), _np(perm), _np(sorted_codes)
+        o = _np(out)
+        n = v.shape[1]
+        if n == 0:
+            return
+        heads = np.flatnonzero(np.concatenate(([True], sc[1:] != sc[:-1])))
+        bounds = np.concatenate((heads, [n]))
+        sv = v[:, p]
+        res = np.empty_like(sv)
+        isf = sv.dtype.kind == "f"
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            seg = sv[:, lo:hi]
+            if kind == 0:
+                wide = seg.astype(np.float64 if isf else np.int64)
+                if skipna and isf:
+                    wide = np.where(np.isnan(wide), 0.0, wide)
+                res[:, lo:hi] = np.cumsum(wide, axis=1).astype(sv.dtype)
+            else:
+                if isf:
+                    idx = np.where(np.isnan(seg), 0, np.arange(hi - lo))
+                    np.maximum.accumulate(idx, axis=1, out=idx)
+                    res[:, lo:hi] = np.take_along_axis(seg, idx, axis=1)
+                else:
+                    res[:, lo:hi] = seg
+        o[:, p] = res

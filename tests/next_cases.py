@@ -16,6 +16,7 @@ ARR = np.load(os.path.join(_DIR, "golden_next.npz"), allow_pickle=False)
 QUANT = [c for c in CASES if c["family"] == "quantile"]
 SCAN = [c for c in CASES if c["family"] == "scan"]
 API_QUANT = [c for c in CASES if c["family"] == "api_quantile"]
+API_SCAN = [c for c in CASES if c["family"] == "api_scan"]
 
 
 def ids(cases):
@@ -50,3 +51,43 @@ def check_api_quantile(case, as_torch_device=None):
         res = res.cpu().numpy()
     assert_same(res, ARR[case["result"]], what=case["id"])
     np.testing.assert_array_equal(np.asarray(groups), ARR[case["groups"]])
+
+
+def _scan_tolerance(arr, func):
+    """cumsum / nancumsum of floats: the reference forms ONE running sum over the code-sorted row and subtracts the total
+    preceding each group (aggregate_flox.py:308-316), so its values carry the rounding of that GLOBAL total; the engine
+    scans every group on its own in f64 and rounds once.  The two agree within a few ulps of the largest running total."""
+    if arr.dtype.kind != "f" or "cumsum" not in func:
+        return None
+    eps = np.finfo(arr.dtype).eps
+    scale = float(np.nanmax(np.nancumsum(np.abs(np.nan_to_num(arr)), axis=-1))) if arr.size else 0.0
+    return dict(rtol=4 * eps, atol=4 * eps * scale)
+
+
+def _assert_scan(res, want, arr, func, what):
+    assert res.dtype == want.dtype and res.shape == want.shape, (what, res.dtype, want.dtype, res.shape, want.shape)
+    tol = _scan_tolerance(arr, func)
+    if tol is None:
+        np.testing.assert_array_equal(res, want, err_msg=what)        # integers, ffill / bfill: bit-exact
+    else:
+        np.testing.assert_allclose(res, want, equal_nan=True, err_msg=what, **tol)
+        assert np.array_equal(np.isnan(res), np.isnan(want)), what
+
+
+def check_engine_scan(case):
+    codes, arr = ARR[case["codes"]], ARR[case["array"]]
+    res = getattr(flox_b200.aggregate_b200, case["func"])(codes, arr, axis=arr.ndim - 1)
+    _assert_scan(res, ARR[case["result"]], arr, case["func"], case["id"])
+
+
+def check_api_scan(case, as_torch_device=None):
+    arr, by = ARR[case["array"]], ARR[case["by"]]
+    a, b = arr, by
+    if as_torch_device is not None:
+        import torch
+
+        a, b = torch.as_tensor(arr, device=as_torch_device), torch.as_tensor(by, device=as_torch_device)
+    res = flox_b200.groupby_scan(a, b, func=case["func"], axis=-1)
+    if as_torch_device is not None:
+        res = res.cpu().numpy()
+    _assert_scan(np.asarray(res), ARR[case["result"]], arr, case["func"], case["id"])

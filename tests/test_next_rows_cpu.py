@@ -27,3 +27,23 @@ def test_quantile_argument_errors(emu):  # noqa: F811
     with pytest.raises(NotImplementedError):
         flox_b200.groupby_reduce(flox_b200.ChunkedArray.from_array(x, 3), by, func="median", expected_groups=np.arange(3),
                                  method="map-reduce")
+
+
+@pytest.mark.parametrize("case", N.SCAN, ids=N.ids(N.SCAN))
+def test_engine_scans(case, emu):  # noqa: F811
+    N.check_engine_scan(case)
+
+
+@pytest.mark.parametrize("case", N.API_SCAN, ids=N.ids(N.API_SCAN))
+def test_api_groupby_scan(case, emu):  # noqa: F811
+    N.check_api_scan(case)
+
+
+def test_groupby_scan_argument_errors(emu):  # noqa: F811
+    x, by = np.arange(6.0), np.array([0, 0, 1, 1, 2, 2])
+    with pytest.raises(NotImplementedError):
+        flox_b200.groupby_scan(x, by, func="cumsum", expected_groups=[0, 1, 2])
+    with pytest.raises(NotImplementedError):
+        flox_b200.groupby_scan(x, by, func="cumsum", engine="numpy")
+    with pytest.raises(NotImplementedError):
+        flox_b200.groupby_scan(np.ones((2, 6)), by, func="cumsum", axis=(0, 1))
