@@ -87,7 +87,7 @@ def test_scans_across_blocks_vs_numpy(func, dtype):
         heads = np.flatnonzero(np.concatenate(([True], sb[1:] != sb[:-1])))
         want_sorted = np.empty_like(sx)
         if func in ("cumsum", "nancumsum"):
-            z = np.where(np.isnan(sx), 0.0, sx) if (func == "nancumsum" and sx.dtype.kind == "f") else sx
+            z = np.where(np.isnan(sx), 0.0, sx) if sx.dtype.kind == "f" else sx   # cumsum: NaNs are masked in below
             cs = np.cumsum(z, axis=1)
             start_tot = np.concatenate((np.zeros((3, 1), cs.dtype), cs[:, heads[1:] - 1]), axis=1)
             want_sorted = cs - np.repeat(start_tot, np.diff(np.concatenate((heads, [n]))), axis=1)
