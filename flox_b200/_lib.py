@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libflox_b200.so")
 
 F32, F64, I32, I64 = 0, 1, 2, 3
 OP_SUM, OP_PROD, OP_SUMSQ = 0, 1, 2
-FIN_SUM, FIN_NANLEN, FIN_MEAN, FIN_MAX, FIN_MIN, FIN_VAR, FIN_STD, FIN_ARG = range(8)
+FIN_SUM, FIN_NANLEN, FIN_MEAN, FIN_MAX, FIN_MIN, FIN_VAR, FIN_STD, FIN_ARG, FIN_PICK = range(9)
 COMB_SUM, COMB_MAX, COMB_MIN, COMB_PROD, COMB_NANMAX, COMB_NANMIN = range(6)
 
 
@@ -44,6 +44,8 @@ SIGNATURES = {
     "floxb_sqdev": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _i32, _vp]),
     "floxb_group_means": (_i32, [_i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "floxb_argext": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _vp, _vp, _i32, C.POINTER(_i64), _vp, _i32, _vp]),
+    "floxb_firstlast": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _i32, _i32, C.POINTER(_i64), _vp, _i32, _vp]),
+    "floxb_take": (_i32, [_chunks_p, _i64, _i32, _i32, _i64, _i64, _i64, _vp, C.POINTER(_i64), _vp, _i32, _vp]),
     "floxb_finalize": (_i32, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f64, _i64, _i64, _f64, _i64, _i64, _vp, _i64, _vp]),
     "floxb_combine": (_i32, [_i32, _i32, _vp, _i64, _i64, _vp, _vp]),
     "floxb_var_combine": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -40,6 +40,7 @@ class GroupedAccumulators:
         self._minmax: dict[bool, tuple] = {}
         self._var: dict[bool, tuple] = {}
         self._arg: dict[tuple, torch.Tensor] = {}
+        self._pick: dict[tuple, tuple] = {}
         self.k = get_kernels()
         # cross-rank merge of every pass (parallel.Comm); None = single process.  Merging the
         # raw accumulators right after each pass IS flox's combine stage (flox/dask.py:90-144).
@@ -93,7 +94,7 @@ class GroupedAccumulators:
             if px is not None:
                 (t,) = px.merge([t], [how])
             else:
-                {"sum": self.comm.sum_, "min": self.comm.min_}[how](t)
+                {"sum": self.comm.sum_, "min": self.comm.min_, "max": self.comm.max_}[how](t)
         return t
 
     # ---- kernel families -----------------------------------------------------------------
@@ -201,6 +202,23 @@ class GroupedAccumulators:
             # key / nnan are already global, so local candidates are comparable
             self._arg[key_] = self._merge_single(px, idx, "min")
         return self._arg[key_]
+
+    def picked(self, is_last: bool, skipna: bool):
+        """(val, cnt, nnan): the value of each group's first / last row (first / last NON-NaN row when skipna), in the wide
+        accumulator dtype.  Positions are global along the reduced axis (index_base), so chunks and ranks merge by MIN / MAX
+        of the position; only the winner's owner writes the value and ranks merge it by SUM over zeros."""
+        key_ = (is_last, skipna)
+        if key_ not in self._pick:
+            cnt, nnan = self.counts()
+            px, pos = self._single(torch.int64)
+            self.k.firstlast(self.chunks, self.A, self.B, self.G, is_last, skipna, self.index_base, pos, init=True,
+                             value_dtype=self.value_dtype)
+            pos = self._merge_single(px, pos, "max" if is_last else "min")
+            px, val = self._single(acc_dtype(self.value_dtype))
+            self.k.take(self.chunks, self.A, self.B, self.G, pos, self.index_base, val, init=True, value_dtype=self.value_dtype)
+            val = self._merge_single(px, val, "sum")
+            self._pick[key_] = (val, cnt, nnan)
+        return self._pick[key_]
 
     # ---- typed results -------------------------------------------------------------------
     def shape(self, lead: tuple[int, ...] = ()):

@@ -30,7 +30,7 @@ from .reductions import evaluate
 __all__ = [
     "sum", "nansum", "prod", "nanprod", "max", "nanmax", "min", "nanmin", "nanlen", "mean", "nanmean",
     "sum_of_squares", "nansum_of_squares", "argmax", "argmin", "nanargmax", "nanargmin", "var", "nanvar", "std", "nanstd",
-    "quantile", "nanquantile", "median", "nanmedian", "cumsum", "nancumsum", "ffill",
+    "quantile", "nanquantile", "median", "nanmedian", "cumsum", "nancumsum", "ffill", "first", "last", "nanfirst", "nanlast",
 ]
 
 
@@ -124,6 +124,10 @@ argmax = _engine("argmax", fixed_dtype=np.int64)
 argmin = _engine("argmin", fixed_dtype=np.int64)
 nanargmax = _engine("nanargmax", fixed_dtype=np.int64)
 nanargmin = _engine("nanargmin", fixed_dtype=np.int64)
+first = _engine("first")
+last = _engine("last")
+nanfirst = _engine("nanfirst")
+nanlast = _engine("nanlast")
 
 
 # ---- sorted-segment family: quantile / median ---------------------------------------------------

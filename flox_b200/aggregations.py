@@ -217,6 +217,11 @@ def _build_reductions() -> dict[str, Aggregation]:
         "min": A("min", chunk="min", combine="min", fill_value=INF, preserves_dtype=True),
         "nanmin": A("nanmin", chunk="nanmin", combine="nanmin", fill_value=INF, final_fill_value=NA, preserves_dtype=True),
     }
+    # first / last (aggregations.py:634-651): positional picks; the nan-skipping pair combines across chunks
+    table["first"] = A("first", chunk=None, combine=None, fill_value=None, preserves_dtype=True)
+    table["last"] = A("last", chunk=None, combine=None, fill_value=None, preserves_dtype=True)
+    table["nanfirst"] = A("nanfirst", chunk="nanfirst", combine="nanfirst", fill_value=NA, preserves_dtype=True)
+    table["nanlast"] = A("nanlast", chunk="nanlast", combine="nanlast", fill_value=NA, preserves_dtype=True)
     # sorted-segment family: only in-memory / blockwise (aggregations.py:672-712: "Support statistical quantities only
     # blockwise")
     table["median"] = A("median", chunk=None, combine=None, fill_value=NA, final_dtype=np.floating)

@@ -434,7 +434,7 @@ def groupby_reduce(array, *by, func, expected_groups=None, sort: bool = True, is
 
     if engine is not None and engine not in ENGINES:
         raise ValueError(f"Expected engine to be one of {list(ENGINES)}. Received {engine} instead.")
-    if func in ("mode", "nanmode", "first", "last", "nanfirst", "nanlast", "all", "any"):
+    if func in ("mode", "nanmode", "all", "any"):
         raise NotImplementedError(f"Reduction {func!r} is outside the b200 engine's scope")
     if func in ("quantile", "nanquantile") and (finalize_kwargs is None or "q" not in finalize_kwargs):
         raise ValueError("Please pass `q` for quantile calculations.")  # core.py:869-871

@@ -73,6 +73,11 @@ k_finalize(int kind, const void* __restrict__ acc_, const void* __restrict__ acc
         r = (OT)v;
         break;
       }
+      case FLOXB_FIN_PICK: {
+        const AccT a = reinterpret_cast<const AccT*>(acc_)[i];
+        r = (rows == 0 || (skipna && c == 0)) ? fill : (OT)a;
+        break;
+      }
       case FLOXB_FIN_ARG: {
         const long long ix = reinterpret_cast<const long long*>(acc_)[i];
         r = (ix == INT64_MAX) ? fill : (OT)ix;

@@ -164,6 +164,39 @@ k_argext_global(const VT* __restrict__ vals, const CT* __restrict__ codes, int64
   }
 }
 
+// ---- first / last -------------------------------------------------------------------------
+// Position of the first (last) row of every group — of the first (last) NON-NaN row when skipna — as a global index
+// along the reduced axis, then a second pass in which the one row whose position won writes its value.  Behind
+// first / last / nanfirst / nanlast (flox/aggregations.py:634-651; numpy_groupies' "first"/"last", xrutils.nanfirst /
+// nanlast flox/xrutils.py:386-412 for the combine).
+template <typename VT, typename CT>
+__global__ void __launch_bounds__(256)
+k_firstlast_pos(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
+                int is_last, int skipna, int64_t index_base, long long* __restrict__ gpos) {
+  const int64_t row_len = n * B;
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    walk_flat<4>(vals + a * row_len, codes, row_len, B, G, [&](VT v, CT c, int64_t i, int64_t b) {
+      if (skipna && is_nan(v)) return;
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;
+      if (is_last) atomicMax(&gpos[bin], (long long)(index_base + i));
+      else atomicMin(&gpos[bin], (long long)(index_base + i));
+    });
+  }
+}
+
+template <typename VT, typename CT>
+__global__ void __launch_bounds__(256)
+k_take_pos(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t B, int64_t G,
+           const long long* __restrict__ gpos, int64_t index_base, typename Acc<VT>::type* __restrict__ gacc) {
+  const int64_t row_len = n * B;
+  for (int64_t a = blockIdx.y; a < A; a += gridDim.y) {
+    walk_flat<4>(vals + a * row_len, codes, row_len, B, G, [&](VT v, CT c, int64_t i, int64_t b) {
+      const int64_t bin = (B == 1) ? a * G + (int64_t)c : (int64_t)c * (A * B) + a * B + b;
+      if (gpos[bin] == (long long)(index_base + i)) gacc[bin] = (typename Acc<VT>::type)v;  // exactly one row per bin
+    });
+  }
+}
+
 __global__ void k_fill_i64(long long* p, int64_t n, long long v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -245,6 +278,45 @@ int launch_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int6
   return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
 }
 
+template <typename VT, typename CT>
+int launch_firstlast(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, int is_last, int skipna,
+                     const int64_t* index_base, int64_t* pos, int init, cudaStream_t st) {
+  const int64_t nbins = A * B * G;
+  if (init && nbins > 0)
+    k_fill_i64<<<fill_blocks(nbins), 256, 0, st>>>(reinterpret_cast<long long*>(pos), nbins, is_last ? INT64_MIN : INT64_MAX);
+  if (nbins == 0) return FLOXB_OK;
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    const floxb_chunk_t& ch = chunks[k];
+    if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+    if (ch.n == 0) continue;
+    k_firstlast_pos<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(
+        reinterpret_cast<const VT*>(ch.values), reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, is_last, skipna,
+        index_base ? index_base[k] : 0, reinterpret_cast<long long*>(pos));
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+template <typename VT, typename CT>
+int launch_take(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int64_t B, int64_t G, const int64_t* pos,
+                const int64_t* index_base, void* acc, int init, cudaStream_t st) {
+  using AccT = typename Acc<VT>::type;
+  const int64_t nbins = A * B * G;
+  if (init && nbins > 0) {
+    if constexpr (is_float<VT>::value) k_fill_f64<<<fill_blocks(nbins), 256, 0, st>>>(reinterpret_cast<double*>(acc), nbins, 0.0);
+    else k_fill_i64<<<fill_blocks(nbins), 256, 0, st>>>(reinterpret_cast<long long*>(acc), nbins, 0LL);
+  }
+  if (nbins == 0) return FLOXB_OK;
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    const floxb_chunk_t& ch = chunks[k];
+    if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
+    if (ch.n == 0) continue;
+    k_take_pos<VT, CT><<<generic_grid(ch.n * B, A), 256, 0, st>>>(
+        reinterpret_cast<const VT*>(ch.values), reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G,
+        reinterpret_cast<const long long*>(pos), index_base ? index_base[k] : 0, reinterpret_cast<AccT*>(acc));
+  }
+  return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
 }  // namespace floxb
 
 using namespace floxb;
@@ -304,4 +376,21 @@ extern "C" int floxb_group_means(int value_dtype, const void* acc, const int64_t
     default: return FLOXB_EDTYPE;
   }
   return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;
+}
+
+extern "C" int floxb_firstlast(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A,
+                               int64_t B, int64_t n_groups, int is_last, int skipna, const int64_t* index_base,
+                               int64_t* acc_pos, int init, void* stream) {
+  if (n_chunks < 0 || A < 0 || B < 0 || n_groups < 0 || (n_chunks > 0 && !chunks)) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && !acc_pos) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FLOXB_DISPATCH_VT_CT(launch_firstlast, chunks, n_chunks, A, B, n_groups, is_last, skipna, index_base, acc_pos, init, st);
+}
+
+extern "C" int floxb_take(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A, int64_t B,
+                          int64_t n_groups, const int64_t* pos, const int64_t* index_base, void* acc, int init, void* stream) {
+  if (n_chunks < 0 || A < 0 || B < 0 || n_groups < 0 || (n_chunks > 0 && !chunks)) return FLOXB_EINVAL;
+  if (A * B * n_groups > 0 && (!pos || !acc)) return FLOXB_EINVAL;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FLOXB_DISPATCH_VT_CT(launch_take, chunks, n_chunks, A, B, n_groups, pos, index_base, acc, init, st);
 }

@@ -201,6 +201,31 @@ class CudaKernels:
         self.launches += 1
         self._scan_launches(chunks, A, B, G, init, 0, vdt, 0, has_smem_path=False)
 
+    def firstlast(self, chunks: Chunks, A: int, B: int, G: int, is_last: bool, skipna: bool, index_base: Sequence[int], pos,
+                  init=True, value_dtype=None):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(pos)
+        if vdt is None:
+            vdt, cdt = value_dtype or torch.float64, torch.int64
+        base = (C.c_int64 * max(len(chunks), 1))(*[int(b) for b in index_base])
+        rc = L.load().floxb_firstlast(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, int(is_last), int(skipna), base,
+                                      self._ptr(pos), int(init), self._stream())
+        L.check(rc, "floxb_firstlast")
+        self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 0, vdt, 0, has_smem_path=False)
+
+    def take(self, chunks: Chunks, A: int, B: int, G: int, pos, index_base: Sequence[int], acc, init=True, value_dtype=None):
+        arr, vdt, cdt = self._chunk_array(chunks, A, B)
+        self._require_cuda(pos, acc)
+        if vdt is None:
+            vdt, cdt = value_dtype or torch.float64, torch.int64
+        base = (C.c_int64 * max(len(chunks), 1))(*[int(b) for b in index_base])
+        rc = L.load().floxb_take(arr, len(chunks), dtype_code(vdt), dtype_code(cdt), A, B, G, self._ptr(pos), base, self._ptr(acc),
+                                 int(init), self._stream())
+        L.check(rc, "floxb_take")
+        self.launches += 1
+        self._scan_launches(chunks, A, B, G, init, 0, vdt, 0, has_smem_path=False)
+
     # -- epilogues -------------------------------------------------------------------------
     def finalize(self, kind: int, value_dtype, acc, acc2, cnt, nnan, skipna: bool, fill, min_count: int, mc_fill,
                  ddof: int, out, group_major_ab: int = 0):

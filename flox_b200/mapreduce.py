@@ -231,7 +231,8 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
         raise NotImplementedError("chunked inputs are grouped by 1-D labels along the chunked (last) axis")
     ctx = parallel.current()
     G = len(expected_groups)
-    chunks, index_base, lead, (A, B), kdt, device = _local_device_chunks(array, by, ctx, need_global_index=_is_arg_reduction(agg),
+    positional = _is_arg_reduction(agg) or agg.name in ("first", "last", "nanfirst", "nanlast")
+    chunks, index_base, lead, (A, B), kdt, device = _local_device_chunks(array, by, ctx, need_global_index=positional,
                                                                          n_groups=G)
     acc = GroupedAccumulators(chunks, A, B, G, kdt, device, index_base=index_base, comm=ctx.comm)
     like = array.chunks[0]
@@ -248,7 +249,7 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
         # final dtype; absent groups are 0 / 0 = NaN like the reference's reindexed intermediates
         funcs, fills, dts = (agg.name,), (0,), (agg.dtype["final"],)
         do_finalize = False
-    elif method == "map-reduce" and not _is_arg_reduction(agg):
+    elif method == "map-reduce" and not positional:
         funcs, fills, dts = agg.chunk, agg.fill_value["intermediate"], agg.dtype["intermediate"]
         do_finalize = True
     else:  # blockwise / cohorts / arg-reductions: straight to the numpy-path value

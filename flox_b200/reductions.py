@@ -22,9 +22,10 @@ _SUMLIKE = {
 }
 _MINMAX = {"max": (True, False), "nanmax": (True, True), "min": (False, False), "nanmin": (False, True)}
 _ARG = {"argmax": (True, False), "nanargmax": (True, True), "argmin": (False, False), "nanargmin": (False, True)}
+_PICK = {"first": (False, False), "last": (True, False), "nanfirst": (False, True), "nanlast": (True, True)}
 _VAR = {"var": (False, False), "nanvar": (True, False), "std": (False, True), "nanstd": (True, True)}
 
-SUPPORTED = tuple(_SUMLIKE) + tuple(_MINMAX) + tuple(_ARG) + tuple(_VAR) + ("nanlen", "mean", "nanmean")
+SUPPORTED = tuple(_SUMLIKE) + tuple(_MINMAX) + tuple(_ARG) + tuple(_VAR) + tuple(_PICK) + ("nanlen", "mean", "nanmean")
 
 _KERNEL_OUT = (torch.float32, torch.float64, torch.int32, torch.int64)
 
@@ -82,6 +83,11 @@ def evaluate(acc: GroupedAccumulators, func: str, *, out_dtype, fill_value=None,
         idx = acc.argext(is_max, skipna)
         _, cnt, nnan = acc.minmax(is_max)
         res = acc.finalize(L.FIN_ARG, idx, None, cnt, nnan, skipna=skipna, **kw)
+    elif func in _PICK:
+        is_last, skipna = _PICK[func]
+        skipna = skipna and acc.value_dtype.is_floating_point
+        val, cnt, nnan = acc.picked(is_last, skipna)
+        res = acc.finalize(L.FIN_PICK, val, None, cnt, nnan, skipna=skipna, **kw)
     elif func in _VAR:
         skipna, std = _VAR[func]
         m2, s, cnt, nnan = acc.var(skipna)

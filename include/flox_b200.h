@@ -55,6 +55,8 @@ extern "C" {
 #define FLOXB_FIN_VAR 5     /* M2/(n-ddof)                     (aggregations.py:460-468)   */
 #define FLOXB_FIN_STD 6     /* sqrt of the above               (aggregations.py:471-472)   */
 #define FLOXB_FIN_ARG 7     /* index acc -> out, fill where no winner                       */
+#define FLOXB_FIN_PICK 8    /* picked value acc -> out (first / last); fill where the group has no row, or (skipna)
+                               no non-NaN row                                    (aggregations.py:634-651) */
 
 /* floxb_combine kind (flox/dask.py:131-143 with agg.simple_combine = np.sum/np.max/np.min) */
 #define FLOXB_COMB_SUM 0
@@ -149,6 +151,18 @@ int floxb_argext(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype,
                  int64_t A, int64_t B, int64_t n_groups, const int64_t* acc_key,
                  const int64_t* nnan, int skipna, const int64_t* index_base /*host, per chunk*/,
                  int64_t* acc_idx, int init, void* stream);
+
+/* first / last / nanfirst / nanlast (flox/aggregations.py:634-651; combine: xrutils.nanfirst / nanlast,
+ * flox/xrutils.py:386-412).  floxb_firstlast: acc_pos[bin] = smallest (is_last: largest) `index_base + i` over the rows of
+ * the group — over its non-NaN rows when skipna; init sets INT64_MAX (INT64_MIN) = "no row".  floxb_take: the row whose
+ * position equals pos[bin] writes its value into acc[bin] (f64 for float values, i64 for integers; init zeroes acc, so that
+ * ranks merge by SUM after merging positions by MIN / MAX). */
+int floxb_firstlast(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A, int64_t B,
+                    int64_t n_groups, int is_last, int skipna, const int64_t* index_base /*host, per chunk*/,
+                    int64_t* acc_pos, int init, void* stream);
+int floxb_take(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype, int64_t A, int64_t B,
+               int64_t n_groups, const int64_t* pos, const int64_t* index_base /*host, per chunk*/, void* acc, int init,
+               void* stream);
 
 /* Typed result from wide accumulators: flox/core.py:410-475 (_finalize_results) pieces that
  * are arithmetic — fill of absent groups (aggregate_flox.py:174-180), NaN propagation,

@@ -225,6 +225,8 @@ class EmuKernels:
                 s = a.astype(np.float32).astype(np.float64) if odt == np.float32 else a.astype(np.float64)
                 s = np.where(rows == 0, np.float64(fillv), np.where(poisoned, np.nan, s))
                 r = (s / c.astype(np.float64)).astype(odt)
+            elif kind == 8:  # PICK
+                r = np.where((rows == 0) | ((c == 0) if skipna else False), fillv, _np(acc).astype(odt))
             elif kind in (3, 4):  # MAX / MIN
                 vdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[value_dtype]
                 v = _key_dec(_np(acc), vdt)
@@ -324,6 +326,28 @@ class EmuKernels:
 
     def widen_codes(self, codes16):
         return codes16.to(torch.int32)
+
+    def firstlast(self, chunks, A, B, G, is_last, skipna, index_base, pos, init=True, value_dtype=None):
+        self.launches += 1
+        p = _np(pos)
+        if init:
+            p[...] = INT64_MIN if is_last else INT64_MAX
+        for (vals, valid, bins), base in zip(self._iter(chunks, A, B, G), index_base):
+            n = vals.shape[1]
+            idx = np.broadcast_to((base + np.arange(n, dtype=np.int64))[None, :, None], vals.shape)
+            ok = valid & ~(np.isnan(vals) if (skipna and vals.dtype.kind == "f") else np.zeros(vals.shape, bool))
+            (np.maximum if is_last else np.minimum).at(p, bins[ok], idx[ok])
+
+    def take(self, chunks, A, B, G, pos, index_base, acc, init=True, value_dtype=None):
+        self.launches += 1
+        a, p = _np(acc), _np(pos)
+        if init:
+            a[...] = 0
+        for (vals, valid, bins), base in zip(self._iter(chunks, A, B, G), index_base):
+            n = vals.shape[1]
+            idx = np.broadcast_to((base + np.arange(n, dtype=np.int64))[None, :, None], vals.shape)
+            hit = valid & (p[bins] == idx)
+            a[bins[hit]] = vals[hit].astype(a.dtype)
 
     # -- sorted-segment family (csrc/segments.cu) ----------------------------------------------------
     def segment_valid(self, sorted_vals, starts, nvalid):

@@ -91,3 +91,54 @@ def check_api_scan(case, as_torch_device=None):
     if as_torch_device is not None:
         res = res.cpu().numpy()
     _assert_scan(np.asarray(res), ARR[case["result"]], arr, case["func"], case["id"])
+
+
+def _first_last_numpy(x, by, G, func):
+    """numpy semantics: the first / last element of each group in order of appearance (numpy_groupies' "first" / "last",
+    the kernels behind flox's first / last); nanfirst / nanlast skip NaNs (flox/xrutils.py:386-412)."""
+    out = np.full(x.shape[:-1] + (G,), np.nan)
+    for g in range(G):
+        sel = x[..., by == g]
+        for idx in np.ndindex(x.shape[:-1]):
+            row = sel[idx]
+            if func.startswith("nan") and row.dtype.kind == "f":
+                row = row[~np.isnan(row)]
+            if row.size:
+                out[idx + (g,)] = row[0] if "first" in func else row[-1]
+    return out
+
+
+def check_first_last(dtype, as_torch_device=None):
+    """No in-repo reference kernel exists for these (engine="flox" falls back to numpy_groupies, absent here): pinned to
+    numpy semantics like the arg-reductions.  In memory, chunked (map-reduce: positions are global, the
+    first occurrence across chunk boundaries wins) and cohorts."""
+    rng = np.random.default_rng(0)
+    n, G = 20_000, 17
+    by = rng.integers(0, G, n)
+    by[by == 3] = 4
+    by[::401] = -1
+    x = (rng.random((3, n)) * 10).astype(dtype)
+    if np.dtype(dtype).kind == "f":
+        x[:, rng.random(n) < 0.3] = np.nan
+        x[1, by == 5] = np.nan
+    valid = np.where(by >= 0, by, G + 5)
+    for func in ("first", "last", "nanfirst", "nanlast"):
+        want = _first_last_numpy(x, valid, G, func)
+        present = ~np.isnan(want) if np.dtype(dtype).kind != "f" else None
+        for mode in ("memory", "map-reduce", "cohorts"):
+            a, b = x, by
+            if as_torch_device is not None:
+                import torch
+
+                a, b = torch.as_tensor(x, device=as_torch_device), torch.as_tensor(by, device=as_torch_device)
+            if mode == "memory":
+                got, _ = flox_b200.groupby_reduce(a, b, func=func, expected_groups=np.arange(G))
+            else:
+                got, _ = flox_b200.groupby_reduce(flox_b200.ChunkedArray.from_array(a, 3001), b, func=func,
+                                                  expected_groups=np.arange(G), method=mode)
+            got = got.cpu().numpy() if as_torch_device is not None else got
+            if present is None:
+                assert got.dtype == np.dtype(dtype)
+                np.testing.assert_array_equal(got, want.astype(dtype), err_msg=f"{func}/{mode}")
+            else:  # integer arrays: absent groups hold the integer fill placeholder
+                np.testing.assert_array_equal(got[present], want[present].astype(got.dtype), err_msg=f"{func}/{mode}")

@@ -120,3 +120,9 @@ def test_scans_across_blocks_vs_numpy(func, dtype):
             np.testing.assert_allclose(got, want.astype(dtype), rtol=1e-6 if dtype == np.float32 else 1e-12, atol=1e-3 if dtype == np.float32 else 1e-9, equal_nan=True)
         else:
             np.testing.assert_array_equal(got, want.astype(got.dtype))
+
+
+@pytest.mark.parametrize("container", ["numpy", "cuda"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+def test_first_last_family(dtype, container):
+    N.check_first_last(dtype, as_torch_device="cuda" if container == "cuda" else None)

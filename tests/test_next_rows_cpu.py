@@ -47,3 +47,8 @@ def test_groupby_scan_argument_errors(emu):  # noqa: F811
         flox_b200.groupby_scan(x, by, func="cumsum", engine="numpy")
     with pytest.raises(NotImplementedError):
         flox_b200.groupby_scan(np.ones((2, 6)), by, func="cumsum", axis=(0, 1))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+def test_first_last_family(dtype, emu):  # noqa: F811
+    N.check_first_last(dtype)
