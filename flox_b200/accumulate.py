@@ -19,8 +19,11 @@ from .kernels import PreparedChunks, acc_dtype, get_kernels
 
 
 class GroupedAccumulators:
+    SPARSE_MAX_CONTESTED = 65536  # more straddling groups than this: a dense all-reduce is the better merge
+
     def __init__(self, chunks: Sequence[tuple[torch.Tensor, torch.Tensor]], A: int, B: int, G: int,
-                 value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None, comm=None):
+                 value_dtype: torch.dtype, device: torch.device, index_base: Sequence[int] | None = None, comm=None,
+                 sparse_merge: bool = False):
         self.chunks = chunks if isinstance(chunks, PreparedChunks) else list(chunks)
         self.A, self.B, self.G = int(A), int(B), int(G)
         self.nbins = self.A * self.B * self.G
@@ -45,6 +48,9 @@ class GroupedAccumulators:
         # cross-rank merge of every pass (parallel.Comm); None = single process.  Merging the
         # raw accumulators right after each pass IS flox's combine stage (flox/dask.py:90-144).
         self.comm = comm if (comm is not None and comm.enabled) else None
+        # Group-sharded output (parallel.distributed(output="sharded")): merge only the groups whose rows straddle ranks.
+        self.sparse_merge = bool(sparse_merge) and self.comm is not None and self.A == 1 and self.B == 1
+        self._contested_idx = False  # False = not determined yet; None = too many (dense merge); LongTensor otherwise
 
     # ---- allocation ----------------------------------------------------------------------
     def _i64(self):
@@ -58,11 +64,45 @@ class GroupedAccumulators:
         both = torch.empty(2 * self.nbins, dtype=torch.int64, device=self.device)
         return both, both[: self.nbins], both[self.nbins:]
 
+    # ---- sparse (cohort-sharded) merge --------------------------------------------------------------------------
+    def _contested(self, cnt, nnan):
+        """Indices of the groups that may have rows on more than one rank, from the ranks' ranges of occupied groups
+        [lo_r, hi_r] (one 16-byte all-gather + one host read, once per accumulator set).  With label-sorted shards —
+        method="cohorts" on sorted labels, BASELINE config 5 — that is at most one group per rank boundary; ranges that
+        overlap widely (random labels) give None and the merge falls back to the dense all-reduce."""
+        if self._contested_idx is not False:
+            return self._contested_idx
+        G = self.nbins
+        idx = torch.arange(G, device=self.device)
+        occupied = (cnt + nnan) > 0
+        pair = torch.stack((torch.where(occupied, idx, G).min(), torch.where(occupied, idx, -1).max()))
+        ranges = [(lo, hi) for lo, hi in self.comm.all_gather_pairs(pair) if hi >= lo]
+        events = sorted([(lo, 1) for lo, _ in ranges] + [(hi + 1, -1) for _, hi in ranges])
+        spans, depth, start = [], 0, None
+        for pos, d in events:           # sweep: maximal intervals covered by >= 2 ranges
+            if depth >= 2 and d < 0 and depth + d < 2 and start is not None:
+                spans.append((start, pos))
+                start = None
+            depth += d
+            if depth >= 2 and start is None:
+                start = pos
+        total = sum(b - a for a, b in spans)
+        if total > self.SPARSE_MAX_CONTESTED:
+            self._contested_idx = None
+        else:
+            self._contested_idx = (torch.cat([torch.arange(a, b, device=self.device) for a, b in spans]) if spans
+                                   else torch.empty(0, dtype=torch.int64, device=self.device))
+        return self._contested_idx
+
+    def _reduce_small(self, t, how: str):
+        {"sum": self.comm.sum_, "prod": self.comm.prod_, "max": self.comm.max_, "min": self.comm.min_}[how](t)
+        return t
+
     def _acc_and_counts(self, dtype: torch.dtype):
         """(px, acc, both, cnt, nnan).  With several ranks and a small bin count the accumulators live in the NVLink
         peer-exchange buffer (px is the PeerExchange): the kernels accumulate straight into it and ONE launch merges
         value accumulator and counters across ranks (flox_b200/exchange.py)."""
-        px = self.comm.peer(24 * self.nbins, self.device) if (self.comm and self.nbins) else None
+        px = self.comm.peer(24 * self.nbins, self.device) if (self.comm and self.nbins and not self.sparse_merge) else None
         if px is not None:
             acc, both = px.views([(dtype, self.nbins), (torch.int64, 2 * self.nbins)])
         else:
@@ -73,6 +113,16 @@ class GroupedAccumulators:
     def _merge(self, px, acc, both, how: str):
         """Cross-rank merge of one pass (flox's combine stage, flox/dask.py:90-144): `how` for the value accumulator,
         sum for the counters.  Returns (acc, cnt, nnan)."""
+        if self.comm and self.sparse_merge and self.nbins:
+            n = self.nbins
+            idx = self._contested(both[:n], both[n:])
+            if idx is not None:
+                if idx.numel():  # every rank computed the same index list: the small collectives line up
+                    acc[idx] = self._reduce_small(acc[idx], how)
+                    small = self._reduce_small(torch.cat((both[:n][idx], both[n:][idx])), "sum")
+                    both[:n][idx] = small[: idx.numel()]
+                    both[n:][idx] = small[idx.numel():]
+                return acc, both[:n], both[n:]
         if self.comm:
             if px is not None:
                 acc, both = px.merge([acc, both], [how, "sum"])
@@ -82,7 +132,7 @@ class GroupedAccumulators:
         return acc, both[: self.nbins], both[self.nbins:]
 
     def _single(self, dtype: torch.dtype):
-        px = self.comm.peer(8 * self.nbins, self.device) if (self.comm and self.nbins) else None
+        px = self.comm.peer(8 * self.nbins, self.device) if (self.comm and self.nbins and not self.sparse_merge) else None
         if px is not None:
             (t,) = px.views([(dtype, self.nbins)])
         else:
@@ -90,6 +140,11 @@ class GroupedAccumulators:
         return px, t
 
     def _merge_single(self, px, t, how: str):
+        if self.comm and self.sparse_merge and self.nbins and self._contested_idx is not False and self._contested_idx is not None:
+            idx = self._contested_idx  # determined by the first pass of this accumulator set (moments / minmax)
+            if idx.numel():
+                t[idx] = self._reduce_small(t[idx], how)
+            return t
         if self.comm:
             if px is not None:
                 (t,) = px.merge([t], [how])

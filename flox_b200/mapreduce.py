@@ -234,7 +234,8 @@ def chunked_groupby_agg(array: ChunkedArray, by, agg: Aggregation, expected_grou
     positional = _is_arg_reduction(agg) or agg.name in ("first", "last", "nanfirst", "nanlast")
     chunks, index_base, lead, (A, B), kdt, device = _local_device_chunks(array, by, ctx, need_global_index=positional,
                                                                          n_groups=G)
-    acc = GroupedAccumulators(chunks, A, B, G, kdt, device, index_base=index_base, comm=ctx.comm)
+    sparse = ctx.output == "sharded" and method in ("cohorts", "blockwise")
+    acc = GroupedAccumulators(chunks, A, B, G, kdt, device, index_base=index_base, comm=ctx.comm, sparse_merge=sparse)
     like = array.chunks[0]
     array_np_dtype = array.dtype
     shape = lead + (G,)

@@ -67,6 +67,15 @@ class Comm:
 
         return peer_exchange(self.group, nbytes, device)
 
+    def all_gather_pairs(self, pair: torch.Tensor) -> list:
+        """[[lo, hi] of every rank] from a 2-element int64 device tensor (one tiny collective + one host read)."""
+        if not self.enabled:
+            return [pair.tolist()]
+        out = torch.empty((self.world_size, 2), dtype=torch.int64, device=pair.device)
+        dist.all_gather_into_tensor(out, pair.reshape(1, 2).contiguous(), group=self.group)
+        self.collectives += 1
+        return out.tolist()
+
     def all_gather_object(self, obj):
         if not self.enabled:
             return [obj]
@@ -123,6 +132,12 @@ class ParallelContext:
 
     comm: Comm = LOCAL
     sharding: str = "replicated"
+    # "replicated": every rank ends with the full result (accumulators all-reduced).
+    # "sharded":    method="cohorts" / "blockwise" only — the result stays sharded BY GROUP like the reference's cohorts
+    #               output stays chunked by cohort (flox/dask.py:469-518): a rank's result is complete for the groups its
+    #               rows touch (boundary groups that straddle ranks are merged and reported by every rank that holds them)
+    #               and holds the fill value elsewhere.  Only the straddling groups cross NVLink.
+    output: str = "replicated"
 
     def my_chunks(self, nchunks: int) -> range:
         if self.sharding == "local" or not self.comm.enabled:
@@ -145,11 +160,13 @@ def current() -> ParallelContext:
 
 
 @contextlib.contextmanager
-def distributed(group=None, sharding: str = "replicated"):
+def distributed(group=None, sharding: str = "replicated", output: str = "replicated"):
     """Run `groupby_reduce` on ChunkedArrays across the ranks of `group` (default: WORLD)."""
     if sharding not in ("replicated", "local"):
         raise ValueError("sharding must be 'replicated' or 'local'")
-    ctx = ParallelContext(Comm(group), sharding)
+    if output not in ("replicated", "sharded"):
+        raise ValueError("output must be 'replicated' or 'sharded'")
+    ctx = ParallelContext(Comm(group), sharding, output)
     token = _current.set(ctx)
     try:
         yield ctx

@@ -74,6 +74,26 @@ def main():
                     got, _ = flox_b200.groupby_reduce(ChunkedArray.from_array(xl, 250_000), ChunkedArray.from_array(bl, 250_000),
                                                       func=func, expected_groups=np.arange(G), method=method, finalize_kwargs=fk)
                 check(f"{func}/{method}/xchg{xchg}", got, want)
+    # group-sharded output: sorted labels, only the groups that straddle ranks are merged; every rank's result is complete
+    # for the groups its rows touch
+    os.environ["FLOXB_PEER_XCHG"] = "1"
+    bys = np.sort(by)
+    mine = np.unique(bys[lo:hi])
+    for func, ddof in (("sum", 0), ("count", 0), ("nanmean", 0), ("nanmax", 0), ("nanvar", 1), ("nanargmax", 0), ("nanlast", 0)):
+        fk = {"ddof": ddof} if ddof else None
+        want, _ = O.groupby_reduce(x, bys, func=func, expected_groups=np.arange(G), ddof=ddof) if func != "nanlast" else (None, None)
+        xl, bl = torch.as_tensor(x[lo:hi], device="cuda"), torch.as_tensor(bys[lo:hi], device="cuda")
+        with parallel.distributed(sharding="local", output="sharded"):
+            got, _ = flox_b200.groupby_reduce(ChunkedArray.from_array(xl, 250_000), ChunkedArray.from_array(bl, 250_000), func=func,
+                                              expected_groups=np.arange(G), method="cohorts", finalize_kwargs=fk)
+        got = got.cpu().numpy()
+        if want is None:
+            continue
+        good = got.dtype == want.dtype and (np.array_equal(got[mine], want[mine]) if want.dtype.kind in "iu" else
+                                            np.allclose(got[mine], want[mine], rtol=1e-6, atol=3e-6, equal_nan=True))
+        if not good:
+            ok = False
+            notes.append(f"[rank {rank}] MISMATCH sharded/{func}")
     # the exchange was really used, and no barrier ever timed out
     used = [ex for ex in exchange._exchanges.values() if ex]
     if not used or used[0].epoch == 0:

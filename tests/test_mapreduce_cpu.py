@@ -138,3 +138,57 @@ def test_two_rank_gloo_merge(tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+_SPARSE_WORKER = r"""
+import os, sys
+sys.path.insert(0, os.environ["FLOXB_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["FLOXB_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=3)
+from flox_b200 import kernels, groupby_reduce, ChunkedArray, parallel
+from tests.emu_backend import EmuKernels
+kernels.set_backend(EmuKernels())
+rank = dist.get_rank()
+rng = np.random.default_rng(11)
+n, G = 9000, 400
+x = rng.standard_normal(n).astype(np.float64); x[::13] = np.nan
+ok = True
+for layout in ("sorted", "random"):
+    by = np.sort(rng.integers(0, G, n)) if layout == "sorted" else rng.integers(0, G, n)
+    by[by == 7] = 8
+    cut = [0, 2950, 6100, n]          # the cuts fall inside groups: boundary groups straddle ranks
+    sl = slice(cut[rank], cut[rank + 1])
+    mine = np.unique(by[sl])
+    for func, fk in (("sum", None), ("count", None), ("nanmean", None), ("nanmax", None), ("nanvar", {"ddof": 1}),
+                     ("nanargmax", None), ("nanfirst", None)):
+        want, _ = groupby_reduce(x, by, func=func, expected_groups=np.arange(G), finalize_kwargs=fk)
+        with parallel.distributed(sharding="local", output="sharded") as ctx:
+            got, _ = groupby_reduce(ChunkedArray.from_array(x[sl], 700), by[sl], func=func, expected_groups=np.arange(G),
+                                    finalize_kwargs=fk, method="cohorts")
+            n_coll = ctx.comm.collectives
+        good = got.dtype == want.dtype and np.allclose(got[mine], want[mine], rtol=1e-12, atol=1e-12, equal_nan=True)
+        if func in ("count", "nanargmax"):
+            good = good and np.array_equal(got[mine], want[mine])
+        if not good:
+            ok = False
+            print("MISMATCH", layout, func, rank, flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_three_rank_gloo_sparse_cohort_merge(tmp_path):
+    """parallel.distributed(output="sharded"): only the groups that straddle ranks are merged (sorted labels), random
+    labels fall back to the dense merge; every rank's result is complete for the groups its rows touch."""
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    script = tmp_path / "sparse_worker.py"
+    script.write_text(_SPARSE_WORKER)
+    port = str(29900 + (os.getpid() % 90))
+    procs = []
+    for rank in range(3):
+        env = dict(os.environ, RANK=str(rank), FLOXB_ROOT=root, FLOXB_PORT=port, OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)

@@ -105,13 +105,16 @@ def main():
         by = torch.sort(torch.randint(lo, min(hi + 1, G), (n,), device=dev, generator=gen)).values  # neighbours share a boundary group
         x = torch.rand(n, device=dev, generator=gen)
         arr, lab = ChunkedArray.from_array(x, 50_000_000), ChunkedArray.from_array(by, 50_000_000)
-        for func in ("sum", "count"):
-            def fn():
-                with parallel.distributed(sharding="local"):
-                    flox_b200.groupby_reduce(arr, lab, func=func, expected_groups=pd.RangeIndex(G), method="cohorts")
-            best, mean = timeit(fn, reps=5, warm=2)
-            report(f"C5 f32[{n * world:.1e}] sorted labels G=1e6 {func} cohorts", n * world, 12, best, mean,
-                   "rows sharded in label order; boundary groups straddle neighbouring ranks")
+        for output in ("sharded", "replicated"):
+            for func in ("sum", "count"):
+                def fn():
+                    with parallel.distributed(sharding="local", output=output):
+                        flox_b200.groupby_reduce(arr, lab, func=func, expected_groups=pd.RangeIndex(G), method="cohorts")
+                best, mean = timeit(fn, reps=5, warm=2)
+                report(f"C5 f32[{n * world:.1e}] sorted labels G=1e6 {func} cohorts, output={output}", n * world, 12, best, mean,
+                       "rows sharded in label order; boundary groups straddle neighbouring ranks; " +
+                       ("only the straddling groups are merged, the result stays sharded by group (dask.py:469-518)"
+                        if output == "sharded" else "the full [G] accumulators are all-reduced"))
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"configs_multi_{world}.json"), "w") as f:
