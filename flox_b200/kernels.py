@@ -43,6 +43,13 @@ class PreparedChunks(list):
     def __init__(self, chunks):
         super().__init__(chunks)
         self.table = None  # (ctypes array, value dtype, code dtype, A, B), filled by CudaKernels._chunk_array
+        self.memo: dict = {}  # facts derived from the LABELS (e.g. which groups straddle ranks), see label_versions
+
+    def label_versions(self) -> tuple:
+        """torch's per-tensor version counters of the label chunks: unchanged versions on unchanged tensor objects mean
+        unchanged label contents, so label-derived facts can be reused (flox memoises its cohort detection the same way,
+        flox/cache.py)."""
+        return tuple(getattr(c, "_version", -1) for _, c in self)
 
 
 class CudaKernels:

@@ -173,6 +173,20 @@ for layout in ("sorted", "random"):
         if not good:
             ok = False
             print("MISMATCH", layout, func, rank, flush=True)
+# kept trailing columns (BASELINE config 4's layout): (n, 4) blocks handed over as block.T, method="blockwise"
+by = np.sort(rng.integers(0, G, n))
+x4 = rng.standard_normal((n, 4)); x4[::9, 2] = np.nan
+sl = slice(cut[rank], cut[rank + 1])
+mine = np.unique(by[sl])
+for func, fk in (("nansum", None), ("nanvar", {"ddof": 1}), ("count", None)):
+    want, _ = groupby_reduce(np.ascontiguousarray(x4.T), by, func=func, expected_groups=np.arange(G), finalize_kwargs=fk)
+    with parallel.distributed(sharding="local", output="sharded"):
+        got, _ = groupby_reduce(ChunkedArray([torch.as_tensor(x4[sl]).t()]), ChunkedArray([torch.as_tensor(by[sl])]), func=func,
+                                expected_groups=np.arange(G), finalize_kwargs=fk, method="blockwise")
+    got = got.numpy()
+    if not (got.shape == want.shape and np.allclose(got[:, mine], want[:, mine], rtol=1e-12, atol=1e-12, equal_nan=True)):
+        ok = False
+        print("MISMATCH B>1", func, rank, flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -89,13 +89,16 @@ def main():
         by = torch.sort(torch.randint(lo, hi, (n,), device=dev, generator=gen)).values
         arr, lab = ChunkedArray([x.t()]), ChunkedArray([by])
         for func in ("nansum", "nanvar"):
+          for output in ("sharded", "replicated"):
             def fn():
-                with parallel.distributed(sharding="local"):
+                with parallel.distributed(sharding="local", output=output):
                     flox_b200.groupby_reduce(arr, lab, func=func, expected_groups=np.arange(G), method="blockwise")
             best, mean = timeit(fn, reps=3, warm=1)
             passes = 2 if "var" in func else 1
-            report(f"C4 f64 (1e8,8) NaNs G=1e5 {func} blockwise", n * world * B * passes, 9, best, mean,
-                   f"{passes} pass(es); rows sharded, every group in one rank's block; [G,8] accumulators merged across ranks")
+            report(f"C4 f64 (1e8,8) NaNs G=1e5 {func} blockwise, output={output}", n * world * B * passes, 9, best, mean,
+                   f"{passes} pass(es); rows sharded, every group in one rank's block; " +
+                   ("nothing to merge: the result stays sharded by group (blockwise, dask.py:390-392)" if output == "sharded"
+                    else "[G,8] accumulators all-reduced"))
         del x, by, arr, lab
         torch.cuda.empty_cache()
 
