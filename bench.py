@@ -350,6 +350,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_cpus = parallel.bind_to_gpu_numa(local)  # before any pinned allocation: staging buffers land on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -578,6 +579,8 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if all_cpus is not None:
+            os.sched_setaffinity(0, all_cpus)  # the reference gets every host core, not only the GPU's NUMA node
         cpu, _, _ = time_cpu(args, args.cpu_seconds, host_chunks)
         if host_chunks is not None:
             # reference leg of the parity gate: the reference's own map-reduce over the sample, same arrays
