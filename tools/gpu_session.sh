@@ -52,6 +52,33 @@ ncuconfigs)
 ncucols)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cols -s 1 -c 1 -f -o gpurun_out/prof_cols \
       python tools/configs_bench.py c3 > gpurun_out/ncu_cols.log 2>&1 ;;
+r2final)  # round-2 final single-GPU session: smoke, the whole -m gpu tier, the driver-shaped bench, the reference arm, ncu
+  python __graft_entry__.py --smoke > gpurun_out/s10_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/s10_smoke.log
+  timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/s10_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s10_pytest.log
+  timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/s10_bench.log 2>&1; echo "rc=$?" >> gpurun_out/s10_bench.log
+  timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/s10_bench_ref.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/s10_launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/s10_ncu_launches.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:bruns -s 2 -c 2 -f -o gpurun_out/prof_c4 \
+      python tools/configs_bench.py c4 > gpurun_out/s10_ncu_c4.log 2>&1 ;;
+ncufx)    # the headline kernel: bench line + ncu --set full
+  timeout 600 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/s3_bench_fx.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_moments_smem_fx -s 1 -c 1 -f -o gpurun_out/prof_fx \
+      python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/s3_ncu.log 2>&1 ;;
+c4ab)     # config 4 with the run-merging kernels and with the round-1 kernels (FLOXB_FORCE_PATH=4)
+  timeout 600 python tools/configs_bench.py c4 > gpurun_out/s2_c4_new.log 2>&1
+  FLOXB_FORCE_PATH=4 timeout 600 python tools/configs_bench.py c4 > gpurun_out/s2_c4_old.log 2>&1 ;;
+breakdown)
+  timeout 600 python tools/step_breakdown.py 1000000000 > gpurun_out/s5_bd1.log 2>&1
+  timeout 600 python tools/step_breakdown.py 125000000 > gpurun_out/s5_bd2.log 2>&1 ;;
+multi)    # run with gpurun --gpus N: parity worker, bench (strong + weak + e2e), configs 3/4/5 on N GPUs
+  NG=$(nvidia-smi -L | wc -l)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
+      tests/dist_worker.py > gpurun_out/s9_dist_$NG.log 2>&1; echo "rc=$?" >> gpurun_out/s9_dist_$NG.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus $NG --steps 20 --warmup 3 > gpurun_out/s9_bench_$NG.log 2>&1; echo "rc=$?" >> gpurun_out/s9_bench_$NG.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 \
+      tools/configs_multi.py ${S9_CONFIGS:-c3 c4 c5} > gpurun_out/s9_configs_$NG.log 2>&1 ;;
 dist)
   NG=$(nvidia-smi -L | wc -l)
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 \
