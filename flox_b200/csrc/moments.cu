@@ -551,7 +551,11 @@ k_moments_global_runs(const VT* __restrict__ vals, const CT* __restrict__ codes,
 // not change (walk_rows_small_b) and issues one RED set per RUN.  Blockwise / sorted labels: ~1 RED set per
 // thread per 64-step segment instead of one per element, the kernel becomes an HBM stream; random labels: one set per
 // element, like k_moments_global.  Accumulators are group-major [G][A*B] like every B > 1 kernel.
-template <typename VT, typename CT, int OP, int B>
+// ROWCNT: the labels are shared by every (a, b), so the number of ROWS of a group is counted once — by the thread of
+// column 0 of a == 0, into that column's count slot — instead of once per element, and the per-(a, b) counts of non-NaN
+// values are rebuilt afterwards as rows - nnan (k_cnt_from_rows).  With random labels (no runs to merge) that is 8 sum
+// REDs + 1 row RED + the NaN REDs per row of 8 instead of 8 + 8 + NaN: the kernel is bound by the L2 atomic rate.
+template <typename VT, typename CT, int OP, int B, bool ROWCNT>
 __global__ void __launch_bounds__(256)
 k_moments_global_bruns(const VT* __restrict__ vals, const CT* __restrict__ codes, int64_t A, int64_t n, int64_t G,
                        typename Acc<VT>::type* __restrict__ gacc, unsigned long long* __restrict__ gcnt,
@@ -569,7 +573,10 @@ k_moments_global_bruns(const VT* __restrict__ vals, const CT* __restrict__ codes
         const int64_t bin = (int64_t)cur * AB + ab;
         if (cn) {
           if constexpr (OP == FLOXB_OP_PROD) atomic_mul(&gacc[bin], s); else atomic_add(&gacc[bin], s);
-          atomicAdd(&gcnt[bin], (unsigned long long)cn);
+          if constexpr (!ROWCNT) atomicAdd(&gcnt[bin], (unsigned long long)cn);
+        }
+        if constexpr (ROWCNT) {
+          if (ab == 0 && (cn + mn)) atomicAdd(&gcnt[bin], (unsigned long long)(cn + mn));  // rows of the group in this run
         }
         if (mn) atomicAdd(&gnan[bin], (unsigned long long)mn);
       }
@@ -586,6 +593,27 @@ k_moments_global_bruns(const VT* __restrict__ vals, const CT* __restrict__ codes
       },
       [&] { flush(); cur = -1; });
   }
+}
+
+// rows <-> counts for the ROWCNT kernels (group-major bins [G][AB]): `to_rows` turns column 0's count into the group's row
+// count before accumulating on top of earlier calls (rows = cnt + nnan), the second form rebuilds every count from it.
+__global__ void k_cnt_to_rows(unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ nnan, int64_t G,
+                              int64_t AB) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x)
+    cnt[g * AB] += nnan[g * AB];
+}
+__global__ void k_cnt_from_rows(unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ nnan, int64_t G,
+                                int64_t AB) {
+  const int64_t total = G * AB;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i / AB, ab = i - g * AB;
+    if (ab != 0) cnt[i] = cnt[g * AB] - nnan[i];   // cnt[g * AB] still holds the rows: column 0 is rewritten below
+  }
+}
+__global__ void k_cnt_from_rows_col0(unsigned long long* __restrict__ cnt, const unsigned long long* __restrict__ nnan, int64_t G,
+                                     int64_t AB) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < G; g += (int64_t)gridDim.x * blockDim.x)
+    cnt[g * AB] -= nnan[g * AB];
 }
 
 template <typename AccT>
@@ -680,6 +708,10 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
       }
     }
   } else {
+    const bool bruns = B > 1 && B <= 32 && (B & (B - 1)) == 0 && force_path != 4;
+    const bool rowcnt = bruns && force_path != 5;  // 5 = per-element counts (testing / profiling)
+    const int rc_blocks = (int)((G + 255) / 256 < 1184 ? (G + 255) / 256 : 1184);
+    if (rowcnt && !init) k_cnt_to_rows<<<rc_blocks, 256, 0, st>>>(gcnt, gnan, G, A * B);
     for (int64_t k = 0; k < n_chunks; ++k) {
       const floxb_chunk_t& ch = chunks[k];
       if (ch.n < 0 || (ch.n > 0 && (!ch.values || !ch.codes))) return FLOXB_EINVAL;
@@ -696,7 +728,7 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
         k_moments_global_runs<VT, CT, OP><<<grid, 256, 0, st>>>(reinterpret_cast<const VT*>(ch.values),
                                                               reinterpret_cast<const CT*>(ch.codes), A, ch.n, G, gacc,
                                                               gcnt, gnan);
-      } else if (B <= 32 && (B & (B - 1)) == 0 && force_path != 4) {
+      } else if (bruns) {
         // small power-of-two B: run-merging kernel, one warp per segment of 64 steps
         const int64_t segs = (ch.n * B + 64 * 32 - 1) / (64 * 32);
         int64_t gx = (segs + 7) / 8;  // 8 warps per block
@@ -706,18 +738,30 @@ int launch_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int64_t A, int
         dim3 g2((unsigned)gx, (unsigned)by);
         const VT* v = reinterpret_cast<const VT*>(ch.values);
         const CT* c = reinterpret_cast<const CT*>(ch.codes);
+#define FLOXB_BRUNS(BB)                                                                                                  \
+  do {                                                                                                                   \
+    if (rowcnt) k_moments_global_bruns<VT, CT, OP, BB, true><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan);     \
+    else k_moments_global_bruns<VT, CT, OP, BB, false><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan);           \
+  } while (0)
         switch (B) {
-          case 2: k_moments_global_bruns<VT, CT, OP, 2><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
-          case 4: k_moments_global_bruns<VT, CT, OP, 4><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
-          case 8: k_moments_global_bruns<VT, CT, OP, 8><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
-          case 16: k_moments_global_bruns<VT, CT, OP, 16><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
-          default: k_moments_global_bruns<VT, CT, OP, 32><<<g2, 256, 0, st>>>(v, c, A, ch.n, G, gacc, gcnt, gnan); break;
+          case 2: FLOXB_BRUNS(2); break;
+          case 4: FLOXB_BRUNS(4); break;
+          case 8: FLOXB_BRUNS(8); break;
+          case 16: FLOXB_BRUNS(16); break;
+          default: FLOXB_BRUNS(32); break;
         }
+#undef FLOXB_BRUNS
       } else {
         k_moments_global<VT, CT, OP><<<grid, 256, 0, st>>>(reinterpret_cast<const VT*>(ch.values),
                                                          reinterpret_cast<const CT*>(ch.codes), A, ch.n, B, G, gacc,
                                                          gcnt, gnan);
       }
+    }
+    if (rowcnt) {
+      const int64_t total = G * A * B;
+      const int fb = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+      k_cnt_from_rows<<<fb, 256, 0, st>>>(gcnt, gnan, G, A * B);
+      k_cnt_from_rows_col0<<<rc_blocks, 256, 0, st>>>(gcnt, gnan, G, A * B);
     }
   }
   return cudaGetLastError() == cudaSuccess ? FLOXB_OK : FLOXB_ECUDA;

@@ -94,7 +94,8 @@ int floxb_max_chunks_per_launch(void);
  *              NaN on the shared-memory f32 path)
  *   init       1 = reset the accumulators first (0 / 1 for PROD), 0 = accumulate on top
  *   force_path 0 = automatic, 1 = shared-memory bins, 2 = L2 atomics, 3 = shared-memory bins with the f32 CAS-loop
- *              level 1 instead of the fixed-point one (testing / profiling)
+ *              level 1 instead of the fixed-point one, 4 = the per-element L2-atomic kernel for small kept trailing
+ *              dims instead of the run-merging one, 5 = run-merging with per-element counts (testing / profiling)
  *   workspace  optional scratch, see floxb_moments_workspace_bytes */
 int floxb_moments(const floxb_chunk_t* chunks, int64_t n_chunks, int value_dtype, int code_dtype,
                   int64_t A, int64_t B, int64_t n_groups, int op, void* acc, int64_t* cnt,
