@@ -72,9 +72,12 @@ class GroupedAccumulators:
         overlap widely (random labels) give None and the merge falls back to the dense all-reduce."""
         if self._contested_idx is not False:
             return self._contested_idx
-        # label-derived: reuse it while the label tensors are unchanged (a loop over the same collection would otherwise
-        # stall on the host read below every call — measured 0.24 ms per call at BASELINE config 5's per-GPU share)
-        memo = getattr(self.chunks, "memo", None)
+        # label-derived: a loop over the same collection would otherwise stall on the host read below every call (measured
+        # 0.24 ms per call at BASELINE config 5's per-GPU share).  Reused only when the caller DECLARED the labels static
+        # (`ChunkedArray.static_labels = True`, like dask graphs are built once for fixed labels and flox memoises its cohort
+        # detection, flox/cache.py): the decision below involves a collective, so every rank must take the same branch —
+        # a rank-local "my labels did not change" test cannot guarantee that.
+        memo = getattr(self.chunks, "memo", None) if getattr(self.chunks, "static_labels", False) else None
         mkey = ("contested", self.comm.world_size, self.comm.rank, self.chunks.label_versions()) if memo is not None else None
         if memo is not None and mkey in memo:
             self._contested_idx = memo[mkey]

@@ -28,6 +28,10 @@ class ChunkedArray:
                 raise ValueError("chunks must agree on all but the last axis")
         self.chunks = chunks
         self._sizes = tuple(int(c.shape[-1]) for c in chunks)
+        # For a ChunkedArray of LABELS: set True to promise that the label values stay as they are, on every rank, for as
+        # long as this object is used — label-derived facts (which groups straddle ranks in the group-sharded merge) are
+        # then computed once instead of on every call.
+        self.static_labels = False
 
     # -- construction ------------------------------------------------------------------------
     @classmethod

@@ -44,6 +44,7 @@ class PreparedChunks(list):
         super().__init__(chunks)
         self.table = None  # (ctypes array, value dtype, code dtype, A, B), filled by CudaKernels._chunk_array
         self.memo: dict = {}  # facts derived from the LABELS (e.g. which groups straddle ranks), see label_versions
+        self.static_labels = False  # the caller's promise that the labels stay as they are on EVERY rank (ChunkedArray.static_labels)
 
     def label_versions(self) -> tuple:
         """torch's per-tensor version counters of the label chunks: unchanged versions on unchanged tensor objects mean

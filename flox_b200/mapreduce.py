@@ -214,7 +214,9 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
                 c = c.to(torch.int64)
         chunks.append((v.reshape(1, -1, B) if time_major else v.view(A, -1, 1), c.view(-1)))
         index_base.append(int(offsets[k]) + start)
-    out = (PreparedChunks(chunks), index_base, lead, (A, B), kdt, device)
+    prepared = PreparedChunks(chunks)
+    prepared.static_labels = bool(getattr(by, "static_labels", False))
+    out = (prepared, index_base, lead, (A, B), kdt, device)
     if not copied and not packed and not need_global_index:
         try:
             array._prepared = (key, by, out)
