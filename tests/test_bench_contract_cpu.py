@@ -48,3 +48,45 @@ def test_own_arm_refuses_to_run_without_cuda():
     p = _run("--gpus", "1", "--steps", "1", "--warmup", "0", "--rows", "400000", "--chunk", "50000")
     assert p.returncode != 0
     assert not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_cpu_arm_reference_and_port_agree_and_port_is_not_slower_by_much():
+    """bench.py's CPU leg: the unmodified reference (baseline/_ref or /root/reference) and the oracle port run the same
+    algorithm — one stable argsort per chunk, reduceat per func, simple_combine, finalize: equal results, and the port's
+    time per chunk stays close to the reference's (round 1's port sorted once per FUNCTION and was 2.3x slower, which
+    inflated every ratio quoted against it)."""
+    import importlib
+    import time
+
+    import numpy as np
+
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("needs /root/reference or baseline/_ref")
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    chunks = bench.cpu_chunks(2, 400_000, 1000, seed=3)
+    bench._REF = None
+    ref = np.asarray(bench.cpu_mapreduce(chunks, 1000, "mean", 2))
+    assert bench.cpu_kind()[0] == "reference"
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    t_ref = best(lambda: bench.cpu_mapreduce(chunks, 1000, "mean", 1))
+    bench._REF = {"error": "forced: exercise the oracle port"}
+    try:
+        port = np.asarray(bench.cpu_mapreduce(chunks, 1000, "mean", 2))
+        assert bench.cpu_kind()[0] == "port"
+        t_port = best(lambda: bench.cpu_mapreduce(chunks, 1000, "mean", 1))
+    finally:
+        bench._REF = None
+    assert port.dtype == ref.dtype
+    np.testing.assert_array_equal(port, ref)       # same algorithm, same order of operations: bit-equal
+    assert t_port < 1.6 * t_ref + 0.05, (t_port, t_ref)
