@@ -509,6 +509,7 @@ def run_gpu(args):
         o_rows_local = args.rows if o_mode == "weak" else args.rows // world
         x, by, arr, lab = make_inputs(o_rows_local)
         o_step = make_step(arr, lab)
+        barrier()  # ranks leave the kernel-only leg at different times (rank 0 also stops the clock sampler)
         for _ in range(max(args.warmup, 3) + 50):
             o_step()
         o_ms, o_res = timed(o_step, args.steps)
@@ -538,6 +539,7 @@ def run_gpu(args):
         del x, by, arr, lab
         torch.cuda.empty_cache()
         harr, hlab = ChunkedArray(hx), ChunkedArray(hb)
+        barrier()  # pinning 12 GB per rank takes different times on different ranks
 
         def e2e_step():
             with parallel.distributed(sharding="local"):

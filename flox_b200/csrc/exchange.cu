@@ -17,8 +17,8 @@
 //     s % 2 for collective s + 2 after its own k_xchg(s + 1) finished, which waited for every peer's epoch s + 1 signal,
 //     which each peer sends after it finished READING in k_xchg(s).  One barrier per collective is therefore enough.
 //
-// A peer that never arrives must not hang the GPU: the spin gives up after ~2 s of clock64() and raises a sticky error
-// word in the local slab header that the host reads back (floxb_xchg_status).
+// A peer that never arrives must not hang the GPU for good: the spin gives up after about a minute of clock64() and raises
+// a sticky error word in the local slab header that the host reads back (floxb_xchg_status).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,6 +26,9 @@
 
 namespace floxb {
 
+// Ranks of one job may legitimately be seconds apart (one is still loading or generating its chunks) — NCCL would simply
+// wait.  The spin therefore waits about a minute of SM clock before it declares the peer dead.
+constexpr long long kBarrierTimeoutCycles = 120000000000LL;  // ~63 s at 1.9 GHz
 constexpr int kMaxPeers = FLOXB_XCHG_MAX_RANKS;
 constexpr int kMaxSegs = FLOXB_XCHG_MAX_SEGMENTS;
 
@@ -73,7 +76,7 @@ k_xchg(const __grid_constant__ XchgArgs a) {
   if (threadIdx.x < a.world) {
     const long long t0 = clock64();
     while (ld_acquire_sys(my_flags + threadIdx.x) < a.epoch) {
-      if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz: a peer died; do not hang the device
+      if (clock64() - t0 > kBarrierTimeoutCycles) {  // a peer died: do not hang the device for good
         s_ok = 0;
         atomicExch(my_err, a.epoch);
         break;

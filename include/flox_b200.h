@@ -273,7 +273,7 @@ int floxb_segment_scan(int kind, const void* values, int value_dtype, const int6
  *       data_offset  byte offset of the buffer in use inside each slab (>= FLOXB_XCHG_HEADER_BYTES, multiple of 8)
  *       seg_words / seg_ops / outs   HOST arrays, n_segments <= FLOXB_XCHG_MAX_SEGMENTS: consecutive runs of 8-byte
  *                    words in the buffer, how to combine each (FLOXB_XCHG_*), and the local device destination of each
- *   floxb_xchg_status *failed_epoch != 0: a barrier gave up waiting (~2 s) for a peer in that collective (the results
+ *   floxb_xchg_status *failed_epoch != 0: a barrier gave up waiting (about a minute) for a peer in that collective (the results
  *                    of it and everything after are undefined).  Synchronises the device. */
 #define FLOXB_XCHG_MAX_RANKS 8
 #define FLOXB_XCHG_MAX_SEGMENTS 4
