@@ -187,15 +187,19 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     # Slabs whose reduced (last) axis is OUTERMOST in memory — a (rows, columns) block handed over as block.T, which is
     # what moving the grouped dim to the end gives (flox/core.py:1014-1018) — are consumed in place as values[1, n, B]
     # (B = the kept columns: BASELINE config 4's layout), like the in-memory path does (aggregate_b200.make_accumulators).
+    # decided from ALL chunks of the collection (not only this rank's): the accumulator layout must be the same on every rank
     time_major = bool(lead) and all(
-        is_torch(array.chunks[k]) and array.chunks[k].device == device and array.chunks[k].dtype == kdt
-        and not array.chunks[k].is_contiguous() and array.chunks[k].movedim(-1, 0).is_contiguous() for k in mine)
+        is_torch(c) and c.device.type == device.type and c.dtype == kdt and not c.is_contiguous()
+        and c.movedim(-1, 0).is_contiguous() for c in array.chunks)
     B = A if time_major else 1
     if time_major:
         A = 1
     for k in mine:  # all value copies are enqueued first: the link is busy while the worker threads pack labels
         v = array.chunks[k]
         if time_major:
+            if v.device != device:
+                copied = True
+                v = v.to(device)
             v = v.movedim(-1, 0)
         elif not (is_torch(v) and v.device == device and v.dtype == kdt and v.is_contiguous()):  # else: already in place
             copied = True
