@@ -162,9 +162,10 @@ def _local_device_chunks(array: ChunkedArray, by, ctx: parallel.ParallelContext,
     device = default_device()
     # Device-resident chunks that need no copy or conversion are prepared ONCE per (array, labels) pair: the views, the
     # C-ABI chunk table and the offsets are reused by every later call (a map-reduce loop over the same dask-like
-    # collection).  Chunk CONTENTS may change between calls, the tensors themselves must not be swapped.
+    # collection).  Chunk CONTENTS may change between calls; swapping a chunk tensor for another one changes the key.
     world = ctx.comm.world_size if ctx.comm.enabled else 1
-    key = (id(by), ctx.sharding, ctx.comm.rank if ctx.comm.enabled else 0, world, str(device))
+    key = (id(by), ctx.sharding, ctx.comm.rank if ctx.comm.enabled else 0, world, str(device),
+           tuple(map(id, array.chunks)), tuple(map(id, by.chunks)) if is_chunked(by) else None)  # swapped chunks = new key
     cached = getattr(array, "_prepared", None)
     if cached is not None and not need_global_index and cached[0] == key and cached[1] is by:
         return cached[2]
